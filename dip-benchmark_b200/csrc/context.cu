@@ -1,0 +1,615 @@
+// Context, image stacks and the host<->device transfer path of libdip_b200.so.
+//
+// Replaces, behind include/dip.h: sycl::queue + malloc_device + q.memcpy().wait()
+// (/root/reference/benchmarks/sycl/benchmark.cpp:260-264, :331-333), cv.UMat(cpu_image) /
+// image.get() (/root/reference/benchmarks/opencv/benchmark.py:42-44, :92-93).
+//
+// Transfer design (north_star "upload/download path"): three streams per ctx (compute,
+// upload, download).  A pinned host buffer goes over PCIe in a single cudaMemcpy2DAsync on
+// its copy stream; a pageable one is cut into slices that are memcpy'ed into two pinned
+// staging slots and sent while the next slice is being staged.  Images remember an
+// outstanding copy with an event, so kernels wait only when they touch such an image.
+#include <algorithm>
+#include <mutex>
+
+#include "dip_internal.h"
+
+namespace dip {
+
+static thread_local std::string g_last_error;
+
+int fail(const dip_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    if (ctx) const_cast<dip_ctx*>(ctx)->last_error = buf;
+    return code;
+}
+
+int fail_cuda(const dip_ctx* ctx, cudaError_t e, const char* what, const char* file, int line) {
+    const char* base = strrchr(file, '/');
+    return fail(ctx, DIP_ERR_CUDA, "CUDA error %d (%s) at %s:%d: %s", (int)e, cudaGetErrorString(e),
+                base ? base + 1 : file, line, what);
+}
+
+int check_pair(dip_ctx* ctx, const dip_image* src, const dip_image* dst, bool allow_inplace) {
+    if (!ctx || !src || !dst) return fail(ctx, DIP_ERR_ARG, "null ctx/src/dst");
+    const ImgView &a = src->v, &b = dst->v;
+    if (a.width != b.width || a.height != b.height || a.channels != b.channels || a.frames != b.frames)
+        return fail(ctx, DIP_ERR_SHAPE, "src %dx%dx%d(x%d) and dst %dx%dx%d(x%d) differ", a.width,
+                    a.height, a.channels, a.frames, b.width, b.height, b.channels, b.frames);
+    if (!allow_inplace && a.base == b.base)
+        return fail(ctx, DIP_ERR_SHAPE, "stencil operations cannot run in place (src == dst)");
+    return DIP_OK;
+}
+
+int begin_op(dip_ctx* ctx, const dip_image* src, dip_image* dst) {
+    DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    dip_image* imgs[2] = {root_of(const_cast<dip_image*>(src)), root_of(dst)};
+    for (dip_image* im : imgs) {
+        if (im && im->copy_pending) {
+            DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, im->copy_done, 0));
+            im->copy_pending = false;
+        }
+    }
+    return DIP_OK;
+}
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+static int new_image(dip_ctx* ctx, dip_image** out) {
+    dip_image* im = new (std::nothrow) dip_image();
+    if (!im) return fail(ctx, DIP_ERR_NOMEM, "out of host memory");
+    im->ctx = ctx;
+    cudaError_t e = cudaEventCreateWithFlags(&im->copy_done, cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+        delete im;
+        return fail_cuda(ctx, e, "cudaEventCreate", __FILE__, __LINE__);
+    }
+    *out = im;
+    return DIP_OK;
+}
+
+// ---- TMA descriptors ------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled encode_tiled_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        // resolved through the runtime so the library has no link-time libcuda dependency
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(p);
+    });
+    return fn;
+}
+
+int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out) {
+    for (const TmapKey& k : img->tmaps)
+        if (k.box_words == box_words && k.box_rows == box_rows) {
+            *out = &k.map;
+            return DIP_OK;
+        }
+    PFN_encodeTiled enc = encode_tiled_fn();
+    if (!enc) return fail(ctx, DIP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    const ImgView& v = img->v;
+    if ((reinterpret_cast<uintptr_t>(v.base) & 15) || (v.pitch & 15) || (v.frame_stride & 15))
+        return fail(ctx, DIP_ERR_ARG, "image base/pitch/frame stride must be 16-byte aligned for TMA");
+    TmapKey key{};
+    key.box_words = box_words;
+    key.box_rows = box_rows;
+    // (x in 4-byte words, y, frame): u32 elements lift the 256-element box limit to 1 KiB rows
+    cuuint64_t dims[3] = {(cuuint64_t)(v.pitch / 4), (cuuint64_t)v.height, (cuuint64_t)v.frames};
+    cuuint64_t strides[2] = {(cuuint64_t)v.pitch, (cuuint64_t)(v.frames > 1 ? v.frame_stride : v.pitch * (size_t)v.height)};
+    if (strides[1] == 0) strides[1] = 16;
+    cuuint32_t box[3] = {(cuuint32_t)box_words, (cuuint32_t)box_rows, 1};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = enc(&key.map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, v.base, dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS)
+        return fail(ctx, DIP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %dx%d pitch %zu box %dx%d",
+                    (int)r, v.width, v.height, v.pitch, box_words, box_rows);
+    img->tmaps.push_back(key);
+    *out = &img->tmaps.back().map;
+    return DIP_OK;
+}
+
+}  // namespace dip
+
+using namespace dip;
+
+extern "C" {
+
+const char* dip_version(void) { return "dip_b200 0.1 (sm_100a)"; }
+
+const char* dip_last_error_string(const dip_ctx* ctx) {
+    if (ctx) return ctx->last_error.c_str();
+    return g_last_error.c_str();
+}
+
+int dip_device_count(int* count) {
+    if (!count) return fail(nullptr, DIP_ERR_ARG, "count is null");
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) {
+        *count = 0;
+        return fail(nullptr, DIP_ERR_NO_DEVICE, "no CUDA device: %s (there is no CPU fallback)",
+                    cudaGetErrorString(e));
+    }
+    *count = n;
+    return DIP_OK;
+}
+
+int dip_init_on_stream(dip_ctx** out, int device, void* cuda_stream) {
+    if (!out) return fail(nullptr, DIP_ERR_ARG, "ctx out pointer is null");
+    *out = nullptr;
+    int n = 0;
+    int rc = dip_device_count(&n);
+    if (rc != DIP_OK) return rc;
+    if (n == 0) return fail(nullptr, DIP_ERR_NO_DEVICE, "no CUDA device (there is no CPU fallback)");
+    if (device < 0 || device >= n) return fail(nullptr, DIP_ERR_ARG, "device %d out of range [0,%d)", device, n);
+    dip_ctx* ctx = new (std::nothrow) dip_ctx();
+    if (!ctx) return fail(nullptr, DIP_ERR_NOMEM, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop{};
+#define INIT_CUDA(expr)                                                           \
+    do {                                                                          \
+        cudaError_t _e = (expr);                                                  \
+        if (_e != cudaSuccess) {                                                  \
+            int _rc = fail_cuda(nullptr, _e, #expr, __FILE__, __LINE__);          \
+            delete ctx;                                                           \
+            return _rc;                                                           \
+        }                                                                         \
+    } while (0)
+    INIT_CUDA(cudaSetDevice(device));
+    INIT_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        delete ctx;
+        return fail(nullptr, DIP_ERR_NO_DEVICE,
+                    "device %d is sm_%d%d; this library is built for sm_100a only (no fallback)", device,
+                    prop.major, prop.minor);
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->l2_bytes = (size_t)prop.l2CacheSize;
+    if (cuda_stream) {
+        ctx->compute = reinterpret_cast<cudaStream_t>(cuda_stream);
+        ctx->own_compute = false;
+    } else {
+        INIT_CUDA(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    }
+    INIT_CUDA(cudaStreamCreateWithFlags(&ctx->upload, cudaStreamNonBlocking));
+    INIT_CUDA(cudaStreamCreateWithFlags(&ctx->download, cudaStreamNonBlocking));
+    INIT_CUDA(cudaStreamCreateWithFlags(&ctx->halo, cudaStreamNonBlocking));
+    INIT_CUDA(cudaEventCreateWithFlags(&ctx->ev_compute, cudaEventDisableTiming));
+    INIT_CUDA(cudaEventCreateWithFlags(&ctx->ev_halo, cudaEventDisableTiming));
+    INIT_CUDA(cudaEventCreate(&ctx->t0));
+    INIT_CUDA(cudaEventCreate(&ctx->t1));
+    ctx->stage_bytes = (size_t)8 << 20;
+    for (int i = 0; i < dip_ctx::kSlots; ++i) {
+        INIT_CUDA(cudaMallocHost(&ctx->stage_up[i], ctx->stage_bytes));
+        INIT_CUDA(cudaMallocHost(&ctx->stage_dn[i], ctx->stage_bytes));
+        INIT_CUDA(cudaEventCreateWithFlags(&ctx->stage_up_free[i], cudaEventDisableTiming));
+        INIT_CUDA(cudaEventCreateWithFlags(&ctx->stage_dn_done[i], cudaEventDisableTiming));
+    }
+#undef INIT_CUDA
+    *out = ctx;
+    return DIP_OK;
+}
+
+int dip_init(dip_ctx** out, int device) { return dip_init_on_stream(out, device, nullptr); }
+
+int dip_shutdown(dip_ctx* ctx) {
+    if (!ctx) return DIP_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->compute);
+    cudaStreamSynchronize(ctx->upload);
+    cudaStreamSynchronize(ctx->download);
+    cudaStreamSynchronize(ctx->halo);
+    for (int i = 0; i < dip_ctx::kSlots; ++i) {
+        if (ctx->stage_up[i]) cudaFreeHost(ctx->stage_up[i]);
+        if (ctx->stage_dn[i]) cudaFreeHost(ctx->stage_dn[i]);
+        if (ctx->stage_up_free[i]) cudaEventDestroy(ctx->stage_up_free[i]);
+        if (ctx->stage_dn_done[i]) cudaEventDestroy(ctx->stage_dn_done[i]);
+    }
+    if (ctx->flush_buf) cudaFree(ctx->flush_buf);
+    if (ctx->d_checksums) cudaFree(ctx->d_checksums);
+    cudaEventDestroy(ctx->ev_compute);
+    cudaEventDestroy(ctx->ev_halo);
+    cudaEventDestroy(ctx->t0);
+    cudaEventDestroy(ctx->t1);
+    if (ctx->own_compute) cudaStreamDestroy(ctx->compute);
+    cudaStreamDestroy(ctx->upload);
+    cudaStreamDestroy(ctx->download);
+    cudaStreamDestroy(ctx->halo);
+    delete ctx;
+    return DIP_OK;
+}
+
+int dip_sync(dip_ctx* ctx) {
+    if (!ctx) return fail(nullptr, DIP_ERR_ARG, "ctx is null");
+    DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    DIP_CUDA(ctx, cudaStreamSynchronize(ctx->upload));
+    DIP_CUDA(ctx, cudaStreamSynchronize(ctx->halo));
+    DIP_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    DIP_CUDA(ctx, cudaStreamSynchronize(ctx->download));
+    return DIP_OK;
+}
+
+int dip_get_device_info(dip_ctx* ctx, dip_device_info* info) {
+    if (!ctx || !info) return fail(ctx, DIP_ERR_ARG, "null argument");
+    cudaDeviceProp prop{};
+    DIP_CUDA(ctx, cudaGetDeviceProperties(&prop, ctx->device));
+    memset(info, 0, sizeof *info);
+    snprintf(info->name, sizeof info->name, "%.127s", prop.name);
+    info->device = ctx->device;
+    info->sm_count = prop.multiProcessorCount;
+    info->cc_major = prop.major;
+    info->cc_minor = prop.minor;
+    info->total_mem = prop.totalGlobalMem;
+    info->l2_bytes = (size_t)prop.l2CacheSize;
+    return DIP_OK;
+}
+
+// ---- images -----------------------------------------------------------------------------
+int dip_image_create_batch(dip_ctx* ctx, int w, int h, int c, int frames, dip_image** out) {
+    if (!ctx || !out) return fail(ctx, DIP_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (w < 1 || h < 1 || frames < 1) return fail(ctx, DIP_ERR_ARG, "bad geometry %dx%d x%d frames", w, h, frames);
+    if (c != 1 && c != 3 && c != 4) return fail(ctx, DIP_ERR_ARG, "channels must be 1, 3 or 4 (got %d)", c);
+    if ((long long)w * c > (1ll << 30)) return fail(ctx, DIP_ERR_ARG, "row too long");
+    dip_image* im = nullptr;
+    int rc = new_image(ctx, &im);
+    if (rc != DIP_OK) return rc;
+    ImgView& v = im->v;
+    v.width = w; v.height = h; v.channels = c; v.frames = frames;
+    v.rowbytes = w * c;
+    v.pitch = round_up((size_t)v.rowbytes, 16);
+    v.frame_stride = v.pitch * (size_t)h;
+    const size_t bytes = v.frame_stride * (size_t)frames;
+    cudaSetDevice(ctx->device);
+    cudaError_t e = cudaMalloc(&im->alloc, bytes);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        dip_image_destroy(im);
+        return fail(ctx, DIP_ERR_NOMEM, "cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    im->owned = true;
+    v.base = static_cast<uint8_t*>(im->alloc);
+    *out = im;
+    return DIP_OK;
+}
+
+int dip_image_create(dip_ctx* ctx, int w, int h, int c, dip_image** out) {
+    return dip_image_create_batch(ctx, w, h, c, 1, out);
+}
+
+int dip_image_wrap(dip_ctx* ctx, void* p, int w, int h, int c, int frames, size_t pitch,
+                   size_t frame_stride, dip_image** out) {
+    if (!ctx || !out || !p) return fail(ctx, DIP_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (w < 1 || h < 1 || frames < 1 || (c != 1 && c != 3 && c != 4))
+        return fail(ctx, DIP_ERR_ARG, "bad geometry %dx%dx%d x%d", w, h, c, frames);
+    if (pitch == 0) pitch = round_up((size_t)w * c, 16);
+    if (frame_stride == 0) frame_stride = pitch * (size_t)h;
+    if (pitch < (size_t)w * c || (pitch & 15) || (frame_stride & 15) || (reinterpret_cast<uintptr_t>(p) & 15))
+        return fail(ctx, DIP_ERR_ARG, "wrapped memory needs a 16-byte aligned base, pitch and frame stride");
+    if (frames > 1 && frame_stride < pitch * (size_t)h) return fail(ctx, DIP_ERR_ARG, "frame stride too small");
+    dip_image* im = nullptr;
+    int rc = new_image(ctx, &im);
+    if (rc != DIP_OK) return rc;
+    im->v = ImgView{static_cast<uint8_t*>(p), pitch, frame_stride, w, h, c, frames, w * c};
+    *out = im;
+    return DIP_OK;
+}
+
+int dip_image_view(dip_ctx* ctx, dip_image* parent, int first, int count, dip_image** out) {
+    if (!ctx || !parent || !out) return fail(ctx, DIP_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (first < 0 || count < 1 || first + count > parent->v.frames)
+        return fail(ctx, DIP_ERR_ARG, "frames [%d,%d) outside stack of %d", first, first + count, parent->v.frames);
+    dip_image* im = nullptr;
+    int rc = new_image(ctx, &im);
+    if (rc != DIP_OK) return rc;
+    im->v = parent->v;
+    im->v.base = parent->v.base + parent->v.frame_stride * (size_t)first;
+    im->v.frames = count;
+    im->parent = parent;
+    *out = im;
+    return DIP_OK;
+}
+
+int dip_image_rows(dip_ctx* ctx, dip_image* parent, int row0, int rows, dip_image** out) {
+    if (!ctx || !parent || !out) return fail(ctx, DIP_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (row0 < 0 || rows < 1 || row0 + rows > parent->v.height)
+        return fail(ctx, DIP_ERR_ARG, "rows [%d,%d) outside image of %d rows", row0, row0 + rows, parent->v.height);
+    dip_image* im = nullptr;
+    int rc = new_image(ctx, &im);
+    if (rc != DIP_OK) return rc;
+    im->v = parent->v;
+    im->v.base = parent->v.base + parent->v.pitch * (size_t)row0;
+    im->v.height = rows;
+    im->parent = parent;
+    *out = im;
+    return DIP_OK;
+}
+
+int dip_image_destroy(dip_image* im) {
+    if (!im) return DIP_OK;
+    if (im->ctx) cudaSetDevice(im->ctx->device);
+    if (im->copy_pending) cudaEventSynchronize(im->copy_done);
+    if (im->copy_done) cudaEventDestroy(im->copy_done);
+    if (im->ipc_mapped && im->alloc) cudaIpcCloseMemHandle(im->alloc);
+    else if (im->owned && im->alloc) cudaFree(im->alloc);
+    delete im;
+    return DIP_OK;
+}
+
+int dip_image_get_info(const dip_image* im, dip_image_info* info) {
+    if (!im || !info) return fail(nullptr, DIP_ERR_ARG, "null argument");
+    info->width = im->v.width; info->height = im->v.height; info->channels = im->v.channels;
+    info->frames = im->v.frames; info->pitch = im->v.pitch; info->frame_stride = im->v.frame_stride;
+    info->device_ptr = im->v.base; info->device = im->ctx ? im->ctx->device : -1;
+    return DIP_OK;
+}
+
+// ---- pinned host memory -----------------------------------------------------------------
+int dip_host_alloc(void** p, size_t bytes) {
+    if (!p) return fail(nullptr, DIP_ERR_ARG, "null argument");
+    cudaError_t e = cudaMallocHost(p, bytes ? bytes : 1);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail(nullptr, DIP_ERR_NOMEM, "cudaMallocHost(%zu): %s", bytes, cudaGetErrorString(e)); }
+    return DIP_OK;
+}
+int dip_host_free(void* p) {
+    if (!p) return DIP_OK;
+    cudaError_t e = cudaFreeHost(p);
+    if (e != cudaSuccess) return fail_cuda(nullptr, e, "cudaFreeHost", __FILE__, __LINE__);
+    return DIP_OK;
+}
+int dip_host_register(void* p, size_t bytes) {
+    if (!p || !bytes) return fail(nullptr, DIP_ERR_ARG, "null argument");
+    cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail_cuda(nullptr, e, "cudaHostRegister", __FILE__, __LINE__); }
+    return DIP_OK;
+}
+int dip_host_unregister(void* p) {
+    if (!p) return DIP_OK;
+    cudaError_t e = cudaHostUnregister(p);
+    if (e != cudaSuccess) { cudaGetLastError(); return fail_cuda(nullptr, e, "cudaHostUnregister", __FILE__, __LINE__); }
+    return DIP_OK;
+}
+
+static bool is_pinned(const void* p) {
+    cudaPointerAttributes a{};
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost;
+}
+
+// ---- upload / download --------------------------------------------------------------------
+// One 2-D copy per frame unless everything is contiguous, in which case a single flat copy.
+static int copy_2d(dip_ctx* ctx, cudaStream_t s, void* dst, size_t dpitch, size_t dframe, const void* src,
+                   size_t spitch, size_t sframe, size_t rowbytes, int rows, int frames, cudaMemcpyKind kind) {
+    const bool flat = dpitch == rowbytes && spitch == rowbytes && (frames == 1 || (dframe == rowbytes * (size_t)rows && sframe == dframe));
+    if (flat) {
+        DIP_CUDA(ctx, cudaMemcpyAsync(dst, src, rowbytes * (size_t)rows * (size_t)frames, kind, s));
+        return DIP_OK;
+    }
+    for (int f = 0; f < frames; ++f)
+        DIP_CUDA(ctx, cudaMemcpy2DAsync(static_cast<uint8_t*>(dst) + dframe * (size_t)f, dpitch,
+                                        static_cast<const uint8_t*>(src) + sframe * (size_t)f, spitch, rowbytes,
+                                        (size_t)rows, kind, s));
+    return DIP_OK;
+}
+
+int dip_upload(dip_ctx* ctx, dip_image* dst_view, const uint8_t* host, size_t host_pitch) {
+    if (!ctx || !dst_view || !host) return fail(ctx, DIP_ERR_ARG, "null argument");
+    DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const ImgView& v = dst_view->v;
+    dip_image* dst = root_of(dst_view);  // copy ordering is tracked on the owning allocation
+    const size_t rowb = (size_t)v.rowbytes;
+    if (host_pitch == 0) host_pitch = rowb;
+    if (host_pitch < rowb) return fail(ctx, DIP_ERR_ARG, "host pitch %zu < row bytes %zu", host_pitch, rowb);
+    // the copy must not overtake kernels still reading/writing dst
+    DIP_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->compute));
+    DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->upload, ctx->ev_compute, 0));
+    if (dst->copy_pending) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->upload, dst->copy_done, 0));
+    if (is_pinned(host)) {
+        int rc = copy_2d(ctx, ctx->upload, v.base, v.pitch, v.frame_stride, host, host_pitch, host_pitch * (size_t)v.height,
+                         rowb, v.height, v.frames, cudaMemcpyHostToDevice);
+        if (rc != DIP_OK) return rc;
+    } else {
+        // pageable: stage row slices through two pinned slots, copy of slice k overlaps staging of k+1
+        const int rows_per_slice = (int)std::max<size_t>(1, ctx->stage_bytes / rowb);
+        int slot = 0;
+        for (int f = 0; f < v.frames; ++f) {
+            for (int y = 0; y < v.height; y += rows_per_slice) {
+                const int rows = std::min(rows_per_slice, v.height - y);
+                DIP_CUDA(ctx, cudaEventSynchronize(ctx->stage_up_free[slot]));
+                uint8_t* st = ctx->stage_up[slot];
+                const uint8_t* hsrc = host + host_pitch * ((size_t)f * v.height + y);
+                if (host_pitch == rowb) memcpy(st, hsrc, rowb * rows);
+                else for (int r = 0; r < rows; ++r) memcpy(st + rowb * r, hsrc + host_pitch * r, rowb);
+                DIP_CUDA(ctx, cudaMemcpy2DAsync(v.base + v.frame_stride * (size_t)f + v.pitch * (size_t)y, v.pitch, st,
+                                                rowb, rowb, rows, cudaMemcpyHostToDevice, ctx->upload));
+                DIP_CUDA(ctx, cudaEventRecord(ctx->stage_up_free[slot], ctx->upload));
+                slot ^= 1;
+            }
+        }
+    }
+    DIP_CUDA(ctx, cudaEventRecord(dst->copy_done, ctx->upload));
+    dst->copy_pending = true;
+    return DIP_OK;
+}
+
+int dip_download(dip_ctx* ctx, const dip_image* src_c, uint8_t* host, size_t host_pitch) {
+    if (!ctx || !src_c || !host) return fail(ctx, DIP_ERR_ARG, "null argument");
+    DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const ImgView& v = src_c->v;
+    dip_image* src = root_of(const_cast<dip_image*>(src_c));
+    const size_t rowb = (size_t)v.rowbytes;
+    if (host_pitch == 0) host_pitch = rowb;
+    if (host_pitch < rowb) return fail(ctx, DIP_ERR_ARG, "host pitch %zu < row bytes %zu", host_pitch, rowb);
+    DIP_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->compute));
+    DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->download, ctx->ev_compute, 0));
+    if (src->copy_pending) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->download, src->copy_done, 0));
+    if (is_pinned(host)) {
+        int rc = copy_2d(ctx, ctx->download, host, host_pitch, host_pitch * (size_t)v.height, v.base, v.pitch, v.frame_stride,
+                         rowb, v.height, v.frames, cudaMemcpyDeviceToHost);
+        if (rc != DIP_OK) return rc;
+        DIP_CUDA(ctx, cudaEventRecord(src->copy_done, ctx->download));
+        src->copy_pending = true;
+    } else {
+        // pageable destination: D2H into pinned slots, drain slot k while slot k+1 is in flight.
+        // The host memcpy needs the data, so this path completes before returning.
+        const int rows_per_slice = (int)std::max<size_t>(1, ctx->stage_bytes / rowb);
+        struct Pending { uint8_t* hdst; int rows; bool live; } pend[dip_ctx::kSlots] = {};
+        int slot = 0;
+        auto drain = [&](int s) -> int {
+            if (!pend[s].live) return DIP_OK;
+            DIP_CUDA(ctx, cudaEventSynchronize(ctx->stage_dn_done[s]));
+            if (host_pitch == rowb) memcpy(pend[s].hdst, ctx->stage_dn[s], rowb * pend[s].rows);
+            else for (int r = 0; r < pend[s].rows; ++r) memcpy(pend[s].hdst + host_pitch * r, ctx->stage_dn[s] + rowb * r, rowb);
+            pend[s].live = false;
+            return DIP_OK;
+        };
+        for (int f = 0; f < v.frames; ++f) {
+            for (int y = 0; y < v.height; y += rows_per_slice) {
+                const int rows = std::min(rows_per_slice, v.height - y);
+                int rc = drain(slot);
+                if (rc != DIP_OK) return rc;
+                DIP_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_dn[slot], rowb, v.base + v.frame_stride * (size_t)f + v.pitch * (size_t)y,
+                                                v.pitch, rowb, rows, cudaMemcpyDeviceToHost, ctx->download));
+                DIP_CUDA(ctx, cudaEventRecord(ctx->stage_dn_done[slot], ctx->download));
+                pend[slot] = Pending{host + host_pitch * ((size_t)f * v.height + y), rows, true};
+                slot ^= 1;
+            }
+        }
+        for (int s = 0; s < dip_ctx::kSlots; ++s) {
+            int rc = drain(s);
+            if (rc != DIP_OK) return rc;
+        }
+    }
+    return DIP_OK;
+}
+
+// ---- timing, counters, L2 flush ---------------------------------------------------------
+int dip_timer_start(dip_ctx* ctx) {
+    if (!ctx) return fail(nullptr, DIP_ERR_ARG, "ctx is null");
+    DIP_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->compute));
+    return DIP_OK;
+}
+
+int dip_timer_stop(dip_ctx* ctx, float* ms) {
+    if (!ctx || !ms) return fail(ctx, DIP_ERR_ARG, "null argument");
+    DIP_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->compute));
+    DIP_CUDA(ctx, cudaEventSynchronize(ctx->t1));
+    DIP_CUDA(ctx, cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return DIP_OK;
+}
+
+int dip_launch_count(const dip_ctx* ctx, uint64_t* n) {
+    if (!ctx || !n) return fail(ctx, DIP_ERR_ARG, "null argument");
+    *n = ctx->launches;
+    return DIP_OK;
+}
+
+int dip_flush_l2(dip_ctx* ctx) {
+    if (!ctx) return fail(nullptr, DIP_ERR_ARG, "ctx is null");
+    DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->flush_buf) {
+        ctx->flush_bytes = std::max<size_t>(ctx->l2_bytes * 2, (size_t)256 << 20);
+        DIP_CUDA(ctx, cudaMalloc(&ctx->flush_buf, ctx->flush_bytes));
+    }
+    return launch_fill(ctx, ctx->flush_buf, ctx->flush_bytes, 0);
+}
+
+int dip_checksum(dip_ctx* ctx, const dip_image* img, uint64_t* per_frame) {
+    if (!ctx || !img || !per_frame) return fail(ctx, DIP_ERR_ARG, "null argument");
+    int rc = begin_op(ctx, img, nullptr);
+    if (rc != DIP_OK) return rc;
+    const int n = img->v.frames;
+    if (ctx->d_checksums_cap < n) {
+        if (ctx->d_checksums) cudaFree(ctx->d_checksums);
+        ctx->d_checksums = nullptr;
+        DIP_CUDA(ctx, cudaMalloc(&ctx->d_checksums, sizeof(uint64_t) * (size_t)n));
+        ctx->d_checksums_cap = n;
+    }
+    DIP_CUDA(ctx, cudaMemsetAsync(ctx->d_checksums, 0, sizeof(uint64_t) * (size_t)n, ctx->compute));
+    rc = launch_checksum(ctx, img->v, ctx->d_checksums);
+    if (rc != DIP_OK) return rc;
+    DIP_CUDA(ctx, cudaMemcpyAsync(per_frame, ctx->d_checksums, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->compute));
+    DIP_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
+    return DIP_OK;
+}
+
+int dip_synth_fill(dip_ctx* ctx, dip_image* img, uint32_t seed, uint64_t first_frame) {
+    if (!ctx || !img) return fail(ctx, DIP_ERR_ARG, "null argument");
+    int rc = begin_op(ctx, nullptr, img);
+    if (rc != DIP_OK) return rc;
+    return launch_synth(ctx, img->v, seed, first_frame);
+}
+
+// ---- IPC + row copies for mosaic bands ---------------------------------------------------
+int dip_image_ipc_export(dip_ctx* ctx, const dip_image* img, dip_ipc_handle* h) {
+    if (!ctx || !img || !h) return fail(ctx, DIP_ERR_ARG, "null argument");
+    if (!img->owned || img->v.base != img->alloc) return fail(ctx, DIP_ERR_ARG, "only whole library-owned images can be exported");
+    static_assert(sizeof(cudaIpcMemHandle_t) <= sizeof(dip_ipc_handle), "handle size");
+    cudaIpcMemHandle_t mh;
+    DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    DIP_CUDA(ctx, cudaIpcGetMemHandle(&mh, img->alloc));
+    memset(h, 0, sizeof *h);
+    memcpy(h->bytes, &mh, sizeof mh);
+    return DIP_OK;
+}
+
+int dip_image_ipc_import(dip_ctx* ctx, const dip_ipc_handle* h, int w, int hgt, int c, int frames, size_t pitch,
+                         size_t frame_stride, dip_image** out) {
+    if (!ctx || !h || !out) return fail(ctx, DIP_ERR_ARG, "null argument");
+    *out = nullptr;
+    cudaIpcMemHandle_t mh;
+    memcpy(&mh, h->bytes, sizeof mh);
+    void* p = nullptr;
+    DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    DIP_CUDA(ctx, cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess));
+    int rc = dip_image_wrap(ctx, p, w, hgt, c, frames, pitch, frame_stride, out);
+    if (rc != DIP_OK) { cudaIpcCloseMemHandle(p); return rc; }
+    (*out)->alloc = p;
+    (*out)->ipc_mapped = true;
+    return DIP_OK;
+}
+
+int dip_copy_rows(dip_ctx* ctx, const dip_image* src, int src_row, dip_image* dst, int dst_row, int rows) {
+    if (!ctx || !src || !dst) return fail(ctx, DIP_ERR_ARG, "null argument");
+    const ImgView &a = src->v, &b = dst->v;
+    if (a.rowbytes != b.rowbytes || a.frames != b.frames) return fail(ctx, DIP_ERR_SHAPE, "row length / frames differ");
+    if (rows < 1 || src_row < 0 || dst_row < 0 || src_row + rows > a.height || dst_row + rows > b.height)
+        return fail(ctx, DIP_ERR_ARG, "row range out of bounds");
+    DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    // ordered after everything enqueued on the compute stream so far
+    DIP_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->compute));
+    DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->halo, ctx->ev_compute, 0));
+    for (int f = 0; f < a.frames; ++f)
+        DIP_CUDA(ctx, cudaMemcpy2DAsync(b.base + b.frame_stride * (size_t)f + b.pitch * (size_t)dst_row, b.pitch,
+                                        a.base + a.frame_stride * (size_t)f + a.pitch * (size_t)src_row, a.pitch,
+                                        (size_t)a.rowbytes, (size_t)rows, cudaMemcpyDefault, ctx->halo));
+    return DIP_OK;
+}
+
+int dip_halo_fence(dip_ctx* ctx) {
+    if (!ctx) return fail(nullptr, DIP_ERR_ARG, "ctx is null");
+    DIP_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->halo));
+    DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ctx->ev_halo, 0));
+    return DIP_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,136 @@
+// Internal declarations shared by the translation units of libdip_b200.so.
+// Nothing here is part of the ABI (see include/dip.h).
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "dip.h"
+
+namespace dip {
+
+// Device-visible description of an image stack (by value in kernel params).
+struct ImgView {
+    uint8_t* base;        // first byte of frame 0, row 0
+    size_t pitch;         // bytes between rows (multiple of 16)
+    size_t frame_stride;  // bytes between frames (multiple of 16)
+    int width, height, channels, frames;
+    int rowbytes;         // width * channels
+};
+
+struct TmapKey {
+    int box_words, box_rows;
+    CUtensorMap map;
+};
+
+}  // namespace dip
+
+struct dip_image {
+    dip_ctx* ctx = nullptr;
+    dip::ImgView v{};
+    void* alloc = nullptr;       // cudaMalloc'ed block when owned
+    bool owned = false;
+    bool ipc_mapped = false;     // opened with cudaIpcOpenMemHandle
+    dip_image* parent = nullptr; // views: the image whose memory is shared (must outlive the view)
+    // A copy (upload/download/halo) touching this image is outstanding on a copy stream.
+    cudaEvent_t copy_done = nullptr;
+    bool copy_pending = false;
+    std::vector<dip::TmapKey> tmaps;  // cached TMA descriptors of this view
+};
+
+struct dip_ctx {
+    int device = -1;
+    cudaStream_t compute = nullptr;  // kernels
+    bool own_compute = true;
+    cudaStream_t upload = nullptr;   // H2D
+    cudaStream_t download = nullptr; // D2H
+    cudaStream_t halo = nullptr;     // peer row copies
+    cudaEvent_t ev_compute = nullptr;  // scratch: "compute reached here"
+    cudaEvent_t ev_halo = nullptr;
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    int sm_count = 0;
+    size_t l2_bytes = 0;
+    uint64_t launches = 0;
+    // pinned staging for pageable host buffers (two slots per direction)
+    static constexpr int kSlots = 2;
+    uint8_t* stage_up[kSlots] = {nullptr, nullptr};
+    uint8_t* stage_dn[kSlots] = {nullptr, nullptr};
+    cudaEvent_t stage_up_free[kSlots] = {nullptr, nullptr};
+    cudaEvent_t stage_dn_done[kSlots] = {nullptr, nullptr};
+    size_t stage_bytes = 0;
+    // scratch
+    uint8_t* flush_buf = nullptr;
+    size_t flush_bytes = 0;
+    uint64_t* d_checksums = nullptr;
+    int d_checksums_cap = 0;
+    std::string last_error;
+};
+
+namespace dip {
+
+// ---- error plumbing -----------------------------------------------------------------
+int fail(const dip_ctx* ctx, int code, const char* fmt, ...);
+int fail_cuda(const dip_ctx* ctx, cudaError_t e, const char* what, const char* file, int line);
+
+#define DIP_CUDA(ctx, expr)                                                       \
+    do {                                                                          \
+        cudaError_t _e = (expr);                                                  \
+        if (_e != cudaSuccess) return dip::fail_cuda((ctx), _e, #expr, __FILE__, __LINE__); \
+    } while (0)
+
+#define DIP_CHECK_LAUNCH(ctx, name)                                               \
+    do {                                                                          \
+        cudaError_t _e = cudaGetLastError();                                      \
+        if (_e != cudaSuccess) return dip::fail_cuda((ctx), _e, name, __FILE__, __LINE__); \
+        (ctx)->launches++;                                                        \
+    } while (0)
+
+// Make the compute stream wait for outstanding copies on the operands, and set the device.
+int begin_op(dip_ctx* ctx, const dip_image* src, dip_image* dst);
+int check_pair(dip_ctx* ctx, const dip_image* src, const dip_image* dst, bool allow_inplace);
+
+// ---- kernels' host launchers (point_ops.cu) -----------------------------------------
+enum PointOp { kCopy = 0, kInvert = 1, kThreshold = 2 };
+int launch_point(dip_ctx* ctx, PointOp op, const ImgView& src, const ImgView& dst, uint8_t thresh,
+                 uint8_t maxval);
+int launch_grayscale(dip_ctx* ctx, const ImgView& src, const ImgView& dst);
+int launch_synth(dip_ctx* ctx, const ImgView& dst, uint32_t seed, uint64_t first_frame);
+int launch_checksum(dip_ctx* ctx, const ImgView& src, uint64_t* d_out);
+int launch_fill(dip_ctx* ctx, uint8_t* p, size_t bytes, uint32_t value);
+
+// ---- stencils (stencil.cu) ------------------------------------------------------------
+// Row geometry of a stencil launch.  The source's rows [valid_y0, valid_y1) are the image
+// for border purposes (outside: reflect-101 / +inf); output rows [out_y0, out_y1) in source
+// row coordinates are written to dst rows starting at dst_y0.
+struct RowGeom {
+    int valid_y0, valid_y1, out_y0, out_y1, dst_y0;
+};
+enum class Morph { Erode, Dilate };
+int stencil_morph(dip_ctx* ctx, Morph m, const dip_image* src, dip_image* dst, const uint8_t* mask,
+                  int mw, int mh, const RowGeom& g);
+int stencil_convolve(dip_ctx* ctx, const dip_image* src, dip_image* dst, const float* k, int kw,
+                     int kh, const RowGeom& g);
+int stencil_convolve_sep(dip_ctx* ctx, const dip_image* src, dip_image* dst, const float* krow,
+                         int kw, const float* kcol, int kh, const RowGeom& g);
+int stencil_gaussian3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g);
+
+// TMA descriptor of an image view seen as a (pitch/4 words, rows, frames) u32 tensor.
+int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out);
+
+inline dip_image* root_of(dip_image* im) {
+    while (im && im->parent) im = im->parent;
+    return im;
+}
+
+inline RowGeom full_geom(const dip_image* src) {
+    return RowGeom{0, src->v.height, 0, src->v.height, 0};
+}
+
+}  // namespace dip

@@ -1,0 +1,306 @@
+// Point operations of libdip_b200.so: copy, inversion, threshold, grayscale, plus the
+// synthetic-input generator and the checksum used by the batch / mosaic configurations.
+//
+// Replaces InvertKernel / GrayscaleKernel / ThresholdKernel
+// (/root/reference/benchmarks/sycl/benchmark.cpp:54-114: one thread per pixel, byte loads) and
+// cv.bitwise_not / cvtColor / threshold (/root/reference/benchmarks/opencv/benchmark.py:95-97).
+//
+// Design: the image stack is a dense byte stream (pitch = rowbytes rounded to 16), so the
+// byte-wise ops run over it as 16-byte vectors: every thread has UNROLL independent
+// 128-bit loads in flight before its first store, streaming (evict-first) cache policy on
+// both sides because every byte is touched exactly once.  Grayscale works on 48-byte groups
+// (16 BGR pixels = 3 vectors) with OpenCV's 15-bit BT.601 weights evaluated by two dp4a per
+// pixel (weights split into high and low bytes), exact for all 2^24 colours.
+#include <algorithm>
+
+#include "dip_internal.h"
+
+namespace dip {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kUnroll = 4;
+
+__device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
+__device__ __forceinline__ void st_stream(uint4* p, const uint4& v) { __stcs(p, v); }
+
+// BT.601 weights in 15-bit fixed point (OpenCV: B 3735, G 19235, R 9798), split in bytes so
+// that Y = (256*dp4a(px, hi) + dp4a(px, lo) + 16384) >> 15.
+//   3735 = 14*256 + 151, 19235 = 75*256 + 35, 9798 = 38*256 + 70
+constexpr uint32_t kWLo0 = 151u | (35u << 8) | (70u << 16);        // pixel in bytes 0..2
+constexpr uint32_t kWHi0 = 14u | (75u << 8) | (38u << 16);
+constexpr uint32_t kWLo1 = kWLo0 << 8;                               // pixel in bytes 1..3
+constexpr uint32_t kWHi1 = kWHi0 << 8;
+
+__device__ __forceinline__ uint32_t luma(uint32_t px, uint32_t wlo, uint32_t whi) {
+    const uint32_t lo = __dp4a(px, wlo, 16384u);
+    const uint32_t hi = __dp4a(px, whi, 0u);
+    return (hi * 256u + lo) >> 15;
+}
+
+template <int OP>
+__device__ __forceinline__ uint32_t point_word(uint32_t x, uint32_t t4, uint32_t m4) {
+    if (OP == kCopy) return x;
+    if (OP == kInvert) return ~x;
+    if (OP == kThreshold) return __vcmpgtu4(x, t4) & m4;
+    // OP == 3: BGRA -> Y,Y,Y,255
+    const uint32_t y = luma(x, kWLo0, kWHi0);
+    return y * 0x00010101u | 0xFF000000u;
+}
+
+template <int OP>
+__device__ __forceinline__ uint4 point_vec(uint4 v, uint32_t t4, uint32_t m4) {
+    v.x = point_word<OP>(v.x, t4, m4);
+    v.y = point_word<OP>(v.y, t4, m4);
+    v.z = point_word<OP>(v.z, t4, m4);
+    v.w = point_word<OP>(v.w, t4, m4);
+    return v;
+}
+
+// Dense stream: one CTA per chunk of kThreads*kUnroll vectors.
+template <int OP>
+__global__ void __launch_bounds__(kThreads) point_flat_kernel(const uint4* __restrict__ src,
+                                                              uint4* __restrict__ dst, size_t nvec,
+                                                              uint32_t t4, uint32_t m4) {
+    const size_t base = (size_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    uint4 v[kUnroll];
+    if (base + (size_t)(kUnroll - 1) * kThreads < nvec) {
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) v[j] = ld_stream(src + base + (size_t)j * kThreads);
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) st_stream(dst + base + (size_t)j * kThreads, point_vec<OP>(v[j], t4, m4));
+    } else {
+#pragma unroll
+        for (int j = 0; j < kUnroll; ++j) {
+            const size_t i = base + (size_t)j * kThreads;
+            if (i < nvec) st_stream(dst + i, point_vec<OP>(ld_stream(src + i), t4, m4));
+        }
+    }
+}
+
+// Strided layouts (wrapped memory whose pitches differ): one vector per thread.
+template <int OP>
+__global__ void __launch_bounds__(kThreads) point_rows_kernel(ImgView src, ImgView dst, int vec_per_row,
+                                                              size_t total, uint32_t t4, uint32_t m4) {
+    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= total) return;
+    const size_t row = i / (size_t)vec_per_row;
+    const int vx = (int)(i - row * (size_t)vec_per_row);
+    const size_t f = row / (size_t)src.height;
+    const size_t y = row - f * (size_t)src.height;
+    const uint4* s = reinterpret_cast<const uint4*>(src.base + f * src.frame_stride + y * src.pitch) + vx;
+    uint4* d = reinterpret_cast<uint4*>(dst.base + f * dst.frame_stride + y * dst.pitch) + vx;
+    *d = point_vec<OP>(*s, t4, m4);
+}
+
+// BGR grayscale: a thread converts one 48-byte group = 16 pixels = 3 vectors.
+__global__ void __launch_bounds__(kThreads) gray3_kernel(ImgView src, ImgView dst, int groups_per_row, size_t total) {
+    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= total) return;
+    const size_t row = i / (size_t)groups_per_row;
+    const int g = (int)(i - row * (size_t)groups_per_row);
+    const size_t f = row / (size_t)src.height;
+    const size_t y = row - f * (size_t)src.height;
+    const uint8_t* srow = src.base + f * src.frame_stride + y * src.pitch;
+    uint8_t* drow = dst.base + f * dst.frame_stride + y * dst.pitch;
+    const int off = g * 48;
+    // vectors past the padded row end are neither read nor written
+    const int padded = (src.rowbytes + 15) & ~15;
+    const int nv = min(3, (padded - off) >> 4);
+    uint32_t w[12];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (j < nv) v = __ldg(reinterpret_cast<const uint4*>(srow + off) + j);
+        w[4 * j + 0] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+    }
+    uint32_t o[12];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // 4 pixels per 3 words
+        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        const uint32_t y0 = luma(a, kWLo0, kWHi0);                          // bytes 0,1,2 of a
+        const uint32_t y1 = luma(__byte_perm(a, b, 0x7543), kWLo0, kWHi0);  // a.3, b.0, b.1
+        const uint32_t y2 = luma(__byte_perm(b, c, 0x7432), kWLo0, kWHi0);  // b.2, b.3, c.0
+        const uint32_t y3 = luma(c, kWLo1, kWHi1);                          // bytes 1,2,3 of c
+        o[3 * q + 0] = y0 * 0x00010101u | (y1 << 24);
+        o[3 * q + 1] = y1 * 0x00000101u | (y2 * 0x01010000u);
+        o[3 * q + 2] = y2 | (y3 * 0x01010100u);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        if (j < nv) __stcs(reinterpret_cast<uint4*>(drow + off) + j, make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+}
+
+// Same integer mix as oracle/dip_oracle.c:orc_mix32 (kept in sync by tests/test_parity_gpu.py).
+__host__ __device__ __forceinline__ uint32_t mix32(uint64_t idx, uint32_t seed) {
+    uint32_t x = (uint32_t)idx ^ ((uint32_t)(idx >> 32) * 0x9E3779B9u) ^ (seed * 0x85EBCA6Bu + 0xC2B2AE35u);
+    x ^= x >> 16; x *= 0x7FEB352Du;
+    x ^= x >> 15; x *= 0x846CA68Bu;
+    x ^= x >> 16;
+    return x;
+}
+
+__global__ void __launch_bounds__(kThreads) synth_kernel(ImgView dst, uint32_t seed, uint64_t first_frame, int vec_per_row,
+                                                         size_t total) {
+    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
+    if (i >= total) return;
+    const size_t row = i / (size_t)vec_per_row;
+    const int vx = (int)(i - row * (size_t)vec_per_row);
+    const size_t f = row / (size_t)dst.height;
+    const size_t y = row - f * (size_t)dst.height;
+    const uint64_t rowbase = ((first_frame + f) * (uint64_t)dst.height + y) * (uint64_t)dst.rowbytes;
+    uint32_t w[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        uint32_t word = 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+            const int x = vx * 16 + k * 4 + b;
+            const uint32_t v = x < dst.rowbytes ? (mix32(rowbase + (uint64_t)x, seed) >> 24) : 0u;
+            word |= v << (8 * b);
+        }
+        w[k] = word;
+    }
+    *(reinterpret_cast<uint4*>(dst.base + f * dst.frame_stride + y * dst.pitch) + vx) = make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+__global__ void __launch_bounds__(kThreads) checksum_kernel(ImgView src, int vec_per_row, size_t vec_per_frame,
+                                                            unsigned long long* __restrict__ out) {
+    // grid.y = frame; grid-stride over the frame's vectors
+    const size_t f = blockIdx.y;
+    unsigned long long acc = 0;
+    for (size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x; i < vec_per_frame; i += (size_t)gridDim.x * kThreads) {
+        const size_t y = i / (size_t)vec_per_row;
+        const int vx = (int)(i - y * (size_t)vec_per_row);
+        const uint4 v = *(reinterpret_cast<const uint4*>(src.base + f * src.frame_stride + y * src.pitch) + vx);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int x = vx * 16 + k * 4 + b;
+                if (x < src.rowbytes) {
+                    const uint64_t pos = (uint64_t)y * (uint64_t)src.rowbytes + (uint64_t)x;
+                    acc += (unsigned long long)(((w[k] >> (8 * b)) & 0xFFu) + 1u) * (unsigned long long)mix32(pos, 0x1234567u);
+                }
+            }
+    }
+#pragma unroll
+    for (int s = 16; s > 0; s >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, s);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out + f, acc);
+}
+
+bool dense_pair(const ImgView& a, const ImgView& b) {
+    const size_t padded = ((size_t)a.rowbytes + 15) & ~(size_t)15;
+    auto dense = [&](const ImgView& v) {
+        return v.pitch == padded && (v.frames == 1 || v.frame_stride == v.pitch * (size_t)v.height);
+    };
+    return dense(a) && dense(b);
+}
+
+template <int OP>
+int launch_point_t(dip_ctx* ctx, const ImgView& src, const ImgView& dst, uint32_t t4, uint32_t m4) {
+    if (dense_pair(src, dst)) {
+        const size_t nvec = src.pitch * (size_t)src.height * (size_t)src.frames / 16;
+        const size_t chunk = (size_t)kThreads * kUnroll;
+        const size_t blocks = (nvec + chunk - 1) / chunk;
+        if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
+        point_flat_kernel<OP><<<(unsigned)blocks, kThreads, 0, ctx->compute>>>(
+            reinterpret_cast<const uint4*>(src.base), reinterpret_cast<uint4*>(dst.base), nvec, t4, m4);
+    } else {
+        const int vpr = (src.rowbytes + 15) / 16;
+        const size_t total = (size_t)vpr * (size_t)src.height * (size_t)src.frames;
+        const size_t blocks = (total + kThreads - 1) / kThreads;
+        if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
+        point_rows_kernel<OP><<<(unsigned)blocks, kThreads, 0, ctx->compute>>>(src, dst, vpr, total, t4, m4);
+    }
+    DIP_CHECK_LAUNCH(ctx, "point kernel");
+    return DIP_OK;
+}
+
+}  // namespace
+
+int launch_point(dip_ctx* ctx, PointOp op, const ImgView& src, const ImgView& dst, uint8_t thresh, uint8_t maxval) {
+    const uint32_t t4 = thresh * 0x01010101u, m4 = maxval * 0x01010101u;
+    switch (op) {
+        case kCopy: return launch_point_t<kCopy>(ctx, src, dst, t4, m4);
+        case kInvert: return launch_point_t<kInvert>(ctx, src, dst, t4, m4);
+        case kThreshold: return launch_point_t<kThreshold>(ctx, src, dst, t4, m4);
+    }
+    return fail(ctx, DIP_ERR_ARG, "bad point op");
+}
+
+int launch_grayscale(dip_ctx* ctx, const ImgView& src, const ImgView& dst) {
+    if (src.channels == 1) return launch_point_t<kCopy>(ctx, src, dst, 0, 0);
+    if (src.channels == 4) return launch_point_t<3>(ctx, src, dst, 0, 0);
+    const int groups = (src.width + 15) / 16;
+    const size_t total = (size_t)groups * (size_t)src.height * (size_t)src.frames;
+    const size_t blocks = (total + kThreads - 1) / kThreads;
+    if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
+    gray3_kernel<<<(unsigned)blocks, kThreads, 0, ctx->compute>>>(src, dst, groups, total);
+    DIP_CHECK_LAUNCH(ctx, "gray3_kernel");
+    return DIP_OK;
+}
+
+int launch_synth(dip_ctx* ctx, const ImgView& dst, uint32_t seed, uint64_t first_frame) {
+    const int vpr = (dst.rowbytes + 15) / 16;
+    const size_t total = (size_t)vpr * (size_t)dst.height * (size_t)dst.frames;
+    const size_t blocks = (total + kThreads - 1) / kThreads;
+    if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
+    synth_kernel<<<(unsigned)blocks, kThreads, 0, ctx->compute>>>(dst, seed, first_frame, vpr, total);
+    DIP_CHECK_LAUNCH(ctx, "synth_kernel");
+    return DIP_OK;
+}
+
+int launch_checksum(dip_ctx* ctx, const ImgView& src, uint64_t* d_out) {
+    const int vpr = (src.rowbytes + 15) / 16;
+    const size_t vpf = (size_t)vpr * (size_t)src.height;
+    if (src.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "more than 65535 frames");
+    const unsigned bx = (unsigned)std::min<size_t>((vpf + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
+    dim3 grid(bx ? bx : 1, (unsigned)src.frames);
+    checksum_kernel<<<grid, kThreads, 0, ctx->compute>>>(src, vpr, vpf, reinterpret_cast<unsigned long long*>(d_out));
+    DIP_CHECK_LAUNCH(ctx, "checksum_kernel");
+    return DIP_OK;
+}
+
+int launch_fill(dip_ctx* ctx, uint8_t* p, size_t bytes, uint32_t value) {
+    DIP_CUDA(ctx, cudaMemsetAsync(p, (int)value, bytes, ctx->compute));
+    return DIP_OK;
+}
+
+}  // namespace dip
+
+using namespace dip;
+
+extern "C" {
+
+int dip_copy(dip_ctx* ctx, const dip_image* src, dip_image* dst) {
+    int rc = check_pair(ctx, src, dst, true);
+    if (rc != DIP_OK) return rc;
+    if ((rc = begin_op(ctx, src, dst)) != DIP_OK) return rc;
+    return launch_point(ctx, kCopy, src->v, dst->v, 0, 0);
+}
+
+int dip_invert(dip_ctx* ctx, const dip_image* src, dip_image* dst) {
+    int rc = check_pair(ctx, src, dst, true);
+    if (rc != DIP_OK) return rc;
+    if ((rc = begin_op(ctx, src, dst)) != DIP_OK) return rc;
+    return launch_point(ctx, kInvert, src->v, dst->v, 0, 0);
+}
+
+int dip_threshold(dip_ctx* ctx, const dip_image* src, dip_image* dst, uint8_t thresh, uint8_t maxval) {
+    int rc = check_pair(ctx, src, dst, true);
+    if (rc != DIP_OK) return rc;
+    if ((rc = begin_op(ctx, src, dst)) != DIP_OK) return rc;
+    return launch_point(ctx, kThreshold, src->v, dst->v, thresh, maxval);
+}
+
+int dip_grayscale(dip_ctx* ctx, const dip_image* src, dip_image* dst) {
+    int rc = check_pair(ctx, src, dst, true);
+    if (rc != DIP_OK) return rc;
+    if ((rc = begin_op(ctx, src, dst)) != DIP_OK) return rc;
+    return launch_grayscale(ctx, src->v, dst->v);
+}
+
+}  // extern "C"

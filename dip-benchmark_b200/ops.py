@@ -1,0 +1,274 @@
+"""Host-side mirror of the reference's operation layer on top of the C-ABI.
+
+``Context`` plays the role of ``sycl::queue`` (sycl/benchmark.cpp:428) and ``Image`` the role
+of ``cv.UMat`` / ``malloc_device`` buffers (opencv/benchmark.py:42-44, sycl:260-262).  Method
+names follow the reference's operation list (opencv/benchmark.py:92-105).  Everything runs on
+the GPU through libdip_b200.so; nothing here computes pixels.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .capi import check, lib
+
+# opencv/benchmark.py:46-72
+CROSS_MASK = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], dtype=np.uint8)
+SQUARE_MASK = np.ones((3, 3), dtype=np.uint8)
+SQUARE_MASK_1X3 = np.ones((1, 3), dtype=np.uint8)
+SQUARE_MASK_3X1 = np.ones((3, 1), dtype=np.uint8)
+BLUR_3X3 = (np.array([[1, 2, 1], [2, 4, 2], [1, 2, 1]], dtype=np.float32) / np.float32(16))
+BLUR_3X3_1X3 = np.array([[0.25, 0.5, 0.25]], dtype=np.float32)
+BLUR_3X3_3X1 = BLUR_3X3_1X3.T.copy()
+_B5 = np.array([1, 4, 6, 4, 1], dtype=np.float32)
+BLUR_5X5 = (np.outer(_B5, _B5) / np.float32(256)).astype(np.float32)
+BLUR_5X5_1X5 = (_B5 / np.float32(16)).reshape(1, 5)
+BLUR_5X5_5X1 = BLUR_5X5_1X5.T.copy()
+
+
+class Image:
+    """A stack of ``frames`` device images (H x W x C interleaved u8)."""
+
+    def __init__(self, ctx: "Context", handle: int, parent: "Image | None" = None):
+        self.ctx = ctx
+        self._h = C.c_void_p(handle)
+        self._parent = parent  # keeps the owning allocation alive
+        info = capi.ImageInfo()
+        check(lib().dip_image_get_info(self._h, C.byref(info)), ctx._h)
+        self.width, self.height, self.channels, self.frames = info.width, info.height, info.channels, info.frames
+        self.pitch, self.frame_stride, self.device_ptr = info.pitch, info.frame_stride, info.device_ptr
+
+    @property
+    def shape(self):
+        base = (self.height, self.width, self.channels)
+        return base if self.frames == 1 else (self.frames,) + base
+
+    @property
+    def nbytes(self) -> int:
+        return self.frames * self.height * self.width * self.channels
+
+    def close(self):
+        if self._h:
+            lib().dip_image_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+    def __del__(self):  # best effort
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # -- transfers (opencv/benchmark.py:92-93) --------------------------------------------
+    def upload(self, array: np.ndarray) -> "Image":
+        a = np.ascontiguousarray(array, dtype=np.uint8)
+        if a.size != self.nbytes:
+            raise ValueError(f"array of {a.shape} does not match image stack {self.shape}")
+        self._keep = a  # borrowed until the next sync
+        check(lib().dip_upload(self.ctx._h, self._h, a.ctypes.data, 0), self.ctx._h)
+        return self
+
+    def download(self, out: np.ndarray | None = None, sync: bool = True) -> np.ndarray:
+        if out is None:
+            out = np.empty(self.shape, dtype=np.uint8)
+        if out.size != self.nbytes or not out.flags.c_contiguous:
+            raise ValueError("bad output array")
+        check(lib().dip_download(self.ctx._h, self._h, out.ctypes.data, 0), self.ctx._h)
+        if sync:
+            self.ctx.sync()
+        return out
+
+    def view(self, first: int, count: int) -> "Image":
+        h = C.c_void_p()
+        check(lib().dip_image_view(self.ctx._h, self._h, first, count, C.byref(h)), self.ctx._h)
+        return Image(self.ctx, h.value, parent=self)
+
+    def rows(self, row0: int, rows: int) -> "Image":
+        h = C.c_void_p()
+        check(lib().dip_image_rows(self.ctx._h, self._h, row0, rows, C.byref(h)), self.ctx._h)
+        return Image(self.ctx, h.value, parent=self)
+
+    def checksum(self) -> list[int]:
+        out = (C.c_uint64 * self.frames)()
+        check(lib().dip_checksum(self.ctx._h, self._h, out), self.ctx._h)
+        return [int(v) for v in out]
+
+    def synth_fill(self, seed: int = 0, first_frame: int = 0) -> "Image":
+        check(lib().dip_synth_fill(self.ctx._h, self._h, seed & 0xFFFFFFFF, first_frame), self.ctx._h)
+        return self
+
+
+class Context:
+    """One GPU, one compute stream, two copy streams (include/dip.h lifecycle group)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        rc = lib().dip_init(C.byref(self._h), device)
+        if rc < 0:
+            self._h = C.c_void_p(None)
+            check(rc, None)
+        self.device = device
+        self._ops = None
+
+    def close(self):
+        if self._h:
+            lib().dip_shutdown(self._h)
+            self._h = C.c_void_p(None)
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def sync(self):
+        check(lib().dip_sync(self._h), self._h)
+
+    def device_info(self) -> dict:
+        info = capi.DeviceInfo()
+        check(lib().dip_get_device_info(self._h, C.byref(info)), self._h)
+        return dict(name=info.name.decode(), device=info.device, sm_count=info.sm_count,
+                    cc=(info.cc_major, info.cc_minor), total_mem=info.total_mem, l2_bytes=info.l2_bytes)
+
+    # -- images ------------------------------------------------------------------------------
+    def image(self, width: int, height: int, channels: int = 3, frames: int = 1) -> Image:
+        h = C.c_void_p()
+        check(lib().dip_image_create_batch(self._h, width, height, channels, frames, C.byref(h)), self._h)
+        return Image(self, h.value)
+
+    def image_like(self, other: Image) -> Image:
+        return self.image(other.width, other.height, other.channels, other.frames)
+
+    def from_array(self, array: np.ndarray) -> Image:
+        """cv.UMat(cpu_image) -- opencv/benchmark.py:42 (array: HxWxC, HxW, or NxHxWxC)."""
+        a = np.asarray(array, dtype=np.uint8)
+        if a.ndim == 2:
+            a = a[:, :, None]
+        if a.ndim == 3:
+            a = a[None]
+        n, hgt, w, c = a.shape
+        img = self.image(w, hgt, c, n)
+        img.upload(a)
+        self.sync()
+        return img
+
+    # -- the operation list ------------------------------------------------------------------
+    def copy(self, src: Image, dst: Image):
+        check(lib().dip_copy(self._h, src._h, dst._h), self._h)
+
+    def invert(self, src: Image, dst: Image):
+        check(lib().dip_invert(self._h, src._h, dst._h), self._h)
+
+    def grayscale(self, src: Image, dst: Image):
+        check(lib().dip_grayscale(self._h, src._h, dst._h), self._h)
+
+    def threshold(self, src: Image, dst: Image, thresh: int = 127, maxval: int = 255):
+        check(lib().dip_threshold(self._h, src._h, dst._h, thresh, maxval), self._h)
+
+    def erode(self, src: Image, dst: Image, mask: np.ndarray):
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        check(lib().dip_erode(self._h, src._h, dst._h, m.ctypes.data, m.shape[1], m.shape[0]), self._h)
+
+    def dilate(self, src: Image, dst: Image, mask: np.ndarray):
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        check(lib().dip_dilate(self._h, src._h, dst._h, m.ctypes.data, m.shape[1], m.shape[0]), self._h)
+
+    def erode_separable(self, src: Image, dst: Image, mask_w: int = 3, mask_h: int = 3):
+        check(lib().dip_erode_separable(self._h, src._h, dst._h, mask_w, mask_h), self._h)
+
+    def convolve(self, src: Image, dst: Image, kernel: np.ndarray):
+        k = np.ascontiguousarray(kernel, dtype=np.float32)
+        if k.ndim == 1:
+            k = k[None]
+        check(lib().dip_convolve(self._h, src._h, dst._h, k.ctypes.data, k.shape[1], k.shape[0]), self._h)
+
+    def convolve_separable(self, src: Image, dst: Image, krow: np.ndarray, kcol: np.ndarray):
+        kr = np.ascontiguousarray(krow, dtype=np.float32).ravel()
+        kc = np.ascontiguousarray(kcol, dtype=np.float32).ravel()
+        check(lib().dip_convolve_separable(self._h, src._h, dst._h, kr.ctypes.data, kr.size, kc.ctypes.data, kc.size), self._h)
+
+    def gaussian_blur3x3(self, src: Image, dst: Image):
+        check(lib().dip_gaussian_blur3x3(self._h, src._h, dst._h), self._h)
+
+    # -- the reference's list as data --------------------------------------------------------
+    def reference_ops(self):
+        """[(description, prefix, Op)] for the 12 device operations, opencv/benchmark.py:94-105."""
+        if self._ops is None:
+            arr = (capi.Op * 12)()
+            n = lib().dip_reference_ops(arr, 12)
+            check(n, self._h)
+            self._ops_arr = arr
+            self._ops = [(lib().dip_reference_op_description(i).decode(), lib().dip_reference_op_prefix(i).decode(), arr[i])
+                         for i in range(n)]
+        return self._ops
+
+    def apply(self, op: capi.Op, src: Image, dst: Image):
+        check(lib().dip_apply(self._h, C.byref(op), src._h, dst._h), self._h)
+
+    def apply_rows(self, op: capi.Op, src: Image, valid_row0: int, valid_rows: int, out_row0: int, out_rows: int,
+                   dst: Image, dst_row0: int = 0):
+        check(lib().dip_apply_rows(self._h, C.byref(op), src._h, valid_row0, valid_rows, out_row0, out_rows, dst._h,
+                                   dst_row0), self._h)
+
+    def run_ops_host(self, host_in: np.ndarray, ops, host_out: list[np.ndarray], chunk_frames: int = 4):
+        """Upload -> every op -> download, pipelined over three streams (dip_run_ops_host)."""
+        a = host_in
+        assert a.dtype == np.uint8 and a.flags.c_contiguous and a.ndim == 4
+        n, hgt, w, c = a.shape
+        arr = (capi.Op * len(ops))(*ops)
+        outs = (C.c_void_p * len(ops))(*[o.ctypes.data for o in host_out])
+        check(lib().dip_run_ops_host(self._h, a.ctypes.data, w, hgt, c, n, arr, len(ops), outs, chunk_frames), self._h)
+
+    # -- timing ---------------------------------------------------------------------------------
+    def timer_start(self):
+        check(lib().dip_timer_start(self._h), self._h)
+
+    def timer_stop(self) -> float:
+        ms = C.c_float()
+        check(lib().dip_timer_stop(self._h, C.byref(ms)), self._h)
+        return float(ms.value)
+
+    def launch_count(self) -> int:
+        n = C.c_uint64()
+        check(lib().dip_launch_count(self._h, C.byref(n)), self._h)
+        return int(n.value)
+
+    def flush_l2(self):
+        check(lib().dip_flush_l2(self._h), self._h)
+
+    # -- pinned host memory -----------------------------------------------------------------------
+    def pinned_empty(self, shape, dtype=np.uint8) -> np.ndarray:
+        nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        check(lib().dip_host_alloc(C.byref(p), nbytes), self._h)
+        buf = (C.c_uint8 * nbytes).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
+        _PINNED[arr.ctypes.data] = p.value
+        return arr
+
+
+_PINNED: dict[int, int] = {}
+
+
+def free_pinned(arr: np.ndarray) -> None:
+    p = _PINNED.pop(arr.ctypes.data, None)
+    if p is not None:
+        lib().dip_host_free(C.c_void_p(p))
+
+
+# (prefix, method name, extra args) in the reference's order -- opencv/benchmark.py:94-105
+REFERENCE_OPS = [
+    ("copy", "copy", ()),
+    ("inversion", "invert", ()),
+    ("grayscale", "grayscale", ()),
+    ("threshold", "threshold", (127, 255)),
+    ("erosion-cross", "erode", (CROSS_MASK,)),
+    ("erosion-square", "erode", (SQUARE_MASK,)),
+    ("erosion-square-separated", "erode_separable", (3, 3)),
+    ("convolution-gaussian-blur-3x3", "convolve", (BLUR_3X3,)),
+    ("convolution-gaussian-blur-3x3-separated", "convolve_separable", (BLUR_3X3_1X3, BLUR_3X3_3X1)),
+    ("convolution-gaussian-blur-5x5", "convolve", (BLUR_5X5,)),
+    ("convolution-gaussian-blur-5x5-separated", "convolve_separable", (BLUR_5X5_1X5, BLUR_5X5_5X1)),
+    ("gaussian-blur-3x3", "gaussian_blur3x3", ()),
+]

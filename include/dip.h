@@ -1,0 +1,249 @@
+/*
+ * dip.h -- C-ABI of the B200-native image-op library (libdip_b200.so).
+ *
+ * This is the drop-in boundary for the dip-benchmark "operation layer": the 14
+ * operations every backend of the reference implements inside its
+ * perform_benchmark closures.  The reference has no FFI of its own; each entry
+ * point below cites the reference call it replaces:
+ *   opencv:N  = /root/reference/benchmarks/opencv/benchmark.py line N (the parity oracle)
+ *   sycl:N    = /root/reference/benchmarks/sycl/benchmark.cpp line N (native call shape)
+ *   vgl:N     = /root/reference/benchmarks/visiongl/benchmark.cpp line N (C call shape)
+ *
+ * Conventions
+ *  - plain C, no exceptions cross the boundary; every function returns a
+ *    dip_status (0 = OK, negative = error) and records a message retrievable
+ *    with dip_last_error_string().
+ *  - images are opaque handles to DEVICE memory owned by the library: row-major
+ *    H x W x C interleaved u8 (C in {1,3,4}, BGR(A) order as cv.imread gives),
+ *    `frames` images stacked in one allocation, rows `pitch` bytes apart
+ *    (pitch = W*C rounded up to 16).  A plain image is a stack of 1 frame; every
+ *    operation processes all frames of its operands in ONE kernel launch.
+ *  - host pointers are borrowed for the duration of the call chain: transfers
+ *    and kernels are stream-ordered and asynchronous; call dip_sync() before
+ *    touching a host buffer handed to dip_upload/dip_download (the reference's
+ *    SYCL backend waits after every call, sycl:335; dip_sync() gives that).
+ *  - one dip_ctx per (host thread, GPU); a ctx is not thread-safe.
+ *  - there is no CPU fallback: without a CUDA device dip_init fails.
+ */
+#ifndef DIP_H_
+#define DIP_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(_WIN32)
+#define DIP_API
+#else
+#define DIP_API __attribute__((visibility("default")))
+#endif
+
+typedef struct dip_ctx dip_ctx;
+typedef struct dip_image dip_image;
+
+typedef enum dip_status {
+    DIP_OK = 0,
+    DIP_ERR_ARG = -1,         /* null / out-of-range argument                         */
+    DIP_ERR_SHAPE = -2,       /* src/dst geometry mismatch, or in-place stencil       */
+    DIP_ERR_UNSUPPORTED = -3, /* valid request this build does not implement          */
+    DIP_ERR_CUDA = -4,        /* CUDA runtime/driver error (message has the detail)   */
+    DIP_ERR_NOMEM = -5,       /* host or device allocation failed                     */
+    DIP_ERR_NO_DEVICE = -6    /* no usable CUDA device: there is no CPU fallback      */
+} dip_status;
+
+typedef struct dip_image_info {
+    int width, height, channels, frames;
+    size_t pitch;        /* bytes between rows                */
+    size_t frame_stride; /* bytes between frames of the stack */
+    void* device_ptr;    /* first byte of frame 0             */
+    int device;
+} dip_image_info;
+
+typedef struct dip_device_info {
+    char name[128];
+    int device, sm_count, cc_major, cc_minor;
+    size_t total_mem, l2_bytes;
+} dip_device_info;
+
+/* ---- lifecycle (sycl::queue creation sycl:428, vglClInit vgl:86) ------------------ */
+DIP_API const char* dip_version(void);
+DIP_API int dip_device_count(int* count);
+DIP_API int dip_init(dip_ctx** ctx, int device);
+/* as dip_init, but compute work is enqueued on the caller's cudaStream_t */
+DIP_API int dip_init_on_stream(dip_ctx** ctx, int device, void* cuda_stream);
+DIP_API int dip_shutdown(dip_ctx* ctx);
+DIP_API int dip_sync(dip_ctx* ctx); /* q.wait() sycl:335 / vglClFlush vgl:24 */
+DIP_API const char* dip_last_error_string(const dip_ctx* ctx); /* ctx may be NULL */
+DIP_API int dip_get_device_info(dip_ctx* ctx, dip_device_info* info);
+
+/* ---- images (sycl::malloc_device sycl:260-262, vglCreateImage vgl:92-93,
+ *      cv.UMat(cpu_image) opencv:42-44) ------------------------------------------- */
+DIP_API int dip_image_create(dip_ctx* ctx, int width, int height, int channels, dip_image** img);
+DIP_API int dip_image_create_batch(dip_ctx* ctx, int width, int height, int channels, int frames,
+                                   dip_image** img);
+/* borrow caller-owned device memory (16-byte aligned base, pitch % 16 == 0) */
+DIP_API int dip_image_wrap(dip_ctx* ctx, void* device_ptr, int width, int height, int channels,
+                           int frames, size_t pitch, size_t frame_stride, dip_image** img);
+/* a view of frames [first, first+count) of a stack; shares memory with the parent */
+DIP_API int dip_image_view(dip_ctx* ctx, dip_image* parent, int first, int count, dip_image** view);
+/* a view of rows [row0, row0+rows) of every frame (row bands of a mosaic) */
+DIP_API int dip_image_rows(dip_ctx* ctx, dip_image* parent, int row0, int rows, dip_image** view);
+DIP_API int dip_image_destroy(dip_image* img);
+DIP_API int dip_image_get_info(const dip_image* img, dip_image_info* info);
+
+/* ---- pinned host buffers for the transfer path -------------------------------- */
+DIP_API int dip_host_alloc(void** ptr, size_t bytes);
+DIP_API int dip_host_free(void* ptr);
+DIP_API int dip_host_register(void* ptr, size_t bytes);
+DIP_API int dip_host_unregister(void* ptr);
+
+/* ---- memory operations -------------------------------------------------------- */
+/* "Upload": cv.UMat(cpu_image) opencv:92, q.memcpy(d_input, image.data) sycl:331,
+ * vglClUpload vgl:119.  host = frames x H rows of W*C bytes, rows host_pitch apart
+ * (0 = tightly packed), frames host_pitch*H apart. */
+DIP_API int dip_upload(dip_ctx* ctx, dip_image* dst, const uint8_t* host, size_t host_pitch);
+/* "Download": image.get() opencv:93, sycl:332, vglClDownload vgl:120 */
+DIP_API int dip_download(dip_ctx* ctx, const dip_image* src, uint8_t* host, size_t host_pitch);
+/* "Copy": cv.copyTo opencv:94 (intended dst = src), q.memcpy(d_output, d_input) sycl:333,
+ * vglClCopy vgl:121 */
+DIP_API int dip_copy(dip_ctx* ctx, const dip_image* src, dip_image* dst);
+
+/* ---- point operations ------------------------------------------------------------ */
+/* "Inversion": cv.bitwise_not opencv:95, InvertKernel sycl:54-69, vglClInvert vgl:122 */
+DIP_API int dip_invert(dip_ctx* ctx, const dip_image* src, dip_image* dst);
+/* "Grayscale": cvtColor BGR2GRAY -> GRAY2BGR opencv:96 (BT.601 15-bit fixed point, exact),
+ * GrayscaleKernel sycl:71-92, vglClGrayscale vgl:123.  4 channels: alpha := 255; 1: copy */
+DIP_API int dip_grayscale(dip_ctx* ctx, const dip_image* src, dip_image* dst);
+/* "Threshold": cv.threshold(image,127,255,THRESH_BINARY) opencv:97,
+ * ThresholdKernel(...,127,255) sycl:94-114,:337, vglClThreshold vgl:124:
+ * dst = src > thresh ? maxval : 0 on every byte */
+DIP_API int dip_threshold(dip_ctx* ctx, const dip_image* src, dip_image* dst, uint8_t thresh,
+                          uint8_t maxval);
+
+/* ---- stencil operations ---------------------------------------------------------- */
+/* "Erosion": cv.erode(image, mask) opencv:98-99 (and the 1x3 / 3x1 calls :77-78),
+ * ErosionKernel(in,out,w,h,c,mask,mw,mh) sycl:116-157,:339-343, vglClErode(img,out,mask,w,h)
+ * vgl:125-127.  mask = mask_h x mask_w row-major bytes (non-zero = tap), anchor = centre,
+ * out-of-image taps ignored (OpenCV's +inf morphology border). */
+DIP_API int dip_erode(dip_ctx* ctx, const dip_image* src, dip_image* dst, const uint8_t* mask,
+                      int mask_w, int mask_h);
+/* cv.dilate, defined but unused by the reference (opencv:80-82) */
+DIP_API int dip_dilate(dip_ctx* ctx, const dip_image* src, dip_image* dst, const uint8_t* mask,
+                       int mask_w, int mask_h);
+/* "Erosion (1x3+3x1)": erosion_separated opencv:76-78,:100, sycl:341-344 -- the two passes
+ * fused in one kernel (row minimum then column minimum through shared memory; no `aux`
+ * round trip).  All-ones 1 x mask_w then mask_h x 1. */
+DIP_API int dip_erode_separable(dip_ctx* ctx, const dip_image* src, dip_image* dst, int mask_w,
+                                int mask_h);
+/* "Convolution": cv.filter2D(image,-1,kernel) opencv:101,103 (and :85-86,:89-90),
+ * ConvolutionKernel(in,out,w,h,c,kernel,kw,kh) sycl:159-202,:346-356,
+ * vglClConvolution(img,out,kernel,w,h) vgl:128-131.  kernel = kh x kw row-major float,
+ * correlation, anchor = centre, BORDER_REFLECT_101, result rounded half-to-even and
+ * saturated.  Kernels whose weights are k/2^s (the benchmark's Gaussians) take the exact
+ * packed-integer path; anything else an fp32 path (within 1 LSB of OpenCV). */
+DIP_API int dip_convolve(dip_ctx* ctx, const dip_image* src, dip_image* dst, const float* kernel,
+                         int kw, int kh);
+/* "Convolution (1xK+Kx1)": convolution_*_separated opencv:84-90,:102,:104, sycl:347-356 --
+ * row pass (1 x kw) rounded to u8 exactly as the reference's `aux` image is, then column
+ * pass (kh x 1), fused in one kernel. */
+DIP_API int dip_convolve_separable(dip_ctx* ctx, const dip_image* src, dip_image* dst,
+                                   const float* krow, int kw, const float* kcol, int kh);
+/* "Gaussian Blur (3x3)": cv.GaussianBlur(image,(3,3),0) opencv:105,
+ * GaussianBlur3x3Kernel sycl:204-252,:358, vglClBlurSq3 vgl:132 -- OpenCV's bit-exact
+ * fixed-point blur: [1 2 1]x[1 2 1]/16 rounded half-up, BORDER_REFLECT_101. */
+DIP_API int dip_gaussian_blur3x3(dip_ctx* ctx, const dip_image* src, dip_image* dst);
+
+/* ---- the reference's operation list as data (opencv:92-105, sycl:331-358) ---------- */
+typedef enum dip_op_kind {
+    DIP_OP_COPY = 0,
+    DIP_OP_INVERT = 1,
+    DIP_OP_GRAYSCALE = 2,
+    DIP_OP_THRESHOLD = 3,
+    DIP_OP_ERODE = 4,
+    DIP_OP_ERODE_SEPARABLE = 5,
+    DIP_OP_CONVOLVE = 6,
+    DIP_OP_CONVOLVE_SEPARABLE = 7,
+    DIP_OP_GAUSSIAN_BLUR3X3 = 8,
+    DIP_OP_DILATE = 9
+} dip_op_kind;
+
+typedef struct dip_op {
+    int kind;              /* dip_op_kind */
+    uint8_t thresh, maxval;
+    const uint8_t* mask;   /* erode / dilate */
+    int mask_w, mask_h;    /* also the all-ones extents of ERODE_SEPARABLE */
+    const float* kernel;   /* convolve, or the row kernel of CONVOLVE_SEPARABLE */
+    int kw, kh;
+    const float* kernel_col; /* column kernel of CONVOLVE_SEPARABLE */
+} dip_op;
+
+/* dst = op(src) for one entry of an operation list */
+DIP_API int dip_apply(dip_ctx* ctx, const dip_op* op, const dip_image* src, dip_image* dst);
+
+/* Fill `ops` (capacity >= 12) with the reference's 12 device operations in its order:
+ * copy, inversion, grayscale, threshold(127,255), erosion cross / square / 1x3+3x1,
+ * convolution 3x3 / 1x3+3x1 / 5x5 / 1x5+5x1 Gaussian, GaussianBlur 3x3.  Mask and kernel
+ * pointers refer to static storage inside the library.  Returns the count (12). */
+DIP_API int dip_reference_ops(dip_op* ops, int capacity);
+/* the reference's file prefix of entry i ("inversion", "erosion-cross", ...) opencv:94-105 */
+DIP_API const char* dip_reference_op_prefix(int i);
+/* the reference's row description of entry i ("Inversion", "Erosion (3x3 Cross Kernel)", ...) */
+DIP_API const char* dip_reference_op_description(int i);
+
+/* ---- batched host pipeline (the measure_time/perform_benchmark loop, opencv:109-114,
+ *      sycl:365-375, taken end to end): for each of `frames` host images upload once,
+ *      run every op of the list input -> output, download every result.  Uploads,
+ *      kernels and downloads of consecutive chunks overlap on three streams through
+ *      pinned staging.  host_out[i] receives op i's `frames` results. --------------- */
+DIP_API int dip_run_ops_host(dip_ctx* ctx, const uint8_t* host_in, int width, int height,
+                             int channels, int frames, const dip_op* ops, int n_ops,
+                             uint8_t* const* host_out, int chunk_frames);
+
+/* ---- device-side timing on the ctx's compute stream (measure_time opencv:26-38,
+ *      sycl:25-39 use a host clock; these are CUDA events) --------------------------- */
+DIP_API int dip_timer_start(dip_ctx* ctx);
+DIP_API int dip_timer_stop(dip_ctx* ctx, float* elapsed_ms); /* synchronises */
+/* number of kernels this ctx has launched since dip_init (bench.py's gpu_launches) */
+DIP_API int dip_launch_count(const dip_ctx* ctx, uint64_t* launches);
+/* write `bytes` of scratch device memory to evict L2 between timed iterations */
+DIP_API int dip_flush_l2(dip_ctx* ctx);
+
+/* ---- synthetic inputs and checksums (BASELINE.json configs 4 and 5) ---------------- */
+/* byte i of frame f := hash32(global byte index, seed) >> 24; frame numbering starts at
+ * first_frame so that shards of one batch are generated independently per GPU */
+DIP_API int dip_synth_fill(dip_ctx* ctx, dip_image* img, uint32_t seed, uint64_t first_frame);
+/* position-weighted 64-bit checksum of every frame's valid bytes -> host array [frames] */
+DIP_API int dip_checksum(dip_ctx* ctx, const dip_image* img, uint64_t* per_frame);
+
+/* ---- multi-GPU mosaic row bands (BASELINE.json config 5) ---------------------------
+ * A band holds rows [row0, row0+rows) of a tall single-frame mosaic plus `halo` rows
+ * above and below.  Interior bands get their halo rows from the neighbour GPUs' bands
+ * over NVLink (peer copies between IPC-mapped allocations); the first and last band
+ * use the operation's own border rule (reflect-101 / +inf). */
+typedef struct dip_ipc_handle { unsigned char bytes[64]; } dip_ipc_handle;
+DIP_API int dip_image_ipc_export(dip_ctx* ctx, const dip_image* img, dip_ipc_handle* handle);
+DIP_API int dip_image_ipc_import(dip_ctx* ctx, const dip_ipc_handle* handle, int width, int height,
+                                 int channels, int frames, size_t pitch, size_t frame_stride,
+                                 dip_image** img);
+/* copy `rows` rows starting at src_row of src into dst starting at dst_row (same width and
+ * channels; src may live on a peer GPU).  Stream-ordered on the ctx's halo stream. */
+DIP_API int dip_copy_rows(dip_ctx* ctx, const dip_image* src, int src_row, dip_image* dst,
+                          int dst_row, int rows);
+/* make the compute stream wait for all halo copies issued so far */
+DIP_API int dip_halo_fence(dip_ctx* ctx);
+/* dst rows [dst_row0, dst_row0+out_rows) = op(src) rows [out_row0, out_row0+out_rows), where
+ * only src rows [valid_row0, valid_row0+valid_rows) exist for border purposes (rows outside
+ * follow the op's border rule: reflect-101 / +inf).  A band with neighbours above and below
+ * passes its halo rows as valid; the first / last band of a mosaic exclude them.  Point
+ * operations ignore the valid range. */
+DIP_API int dip_apply_rows(dip_ctx* ctx, const dip_op* op, const dip_image* src, int valid_row0,
+                           int valid_rows, int out_row0, int out_rows, dip_image* dst,
+                           int dst_row0);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIP_H_ */

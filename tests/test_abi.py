@@ -1,0 +1,65 @@
+"""CPU: the C-ABI library loads and exports every symbol include/dip.h declares; the host-side
+argument handling that needs no device."""
+import ctypes as C
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol(dip):
+    syms = dip.declared_symbols()
+    assert len(syms) >= 40
+    L = dip.lib()
+    for s in syms:
+        assert hasattr(L, s), f"{s} declared in include/dip.h but not exported"
+    # and the binding covers the header, no more, no less
+    assert set(L._dip_signatures) == set(syms)
+
+
+def test_exports_are_plain_c_symbols(dip):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", dip.lib_path()], text=True)
+    exported = {line.split()[-1] for line in out.splitlines() if " T " in line}
+    assert set(dip.declared_symbols()) <= exported
+    assert not [s for s in exported if s.startswith("_Z") and "dip" in s], "C++ symbols leak from the ABI"
+
+
+def test_header_compiles_as_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "dip.h"\nint main(void){ dip_op o; (void)o; return DIP_OK; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o", str(tmp_path / "t.o")])
+
+
+def test_sass_is_blackwell_native(dip):
+    """The stencil kernels must carry TMA loads (UTMALDG) and the packed min instruction."""
+    try:
+        sass = subprocess.check_output(["cuobjdump", "-sass", dip.lib_path()], text=True, stderr=subprocess.DEVNULL)
+    except (OSError, subprocess.CalledProcessError):
+        pytest.skip("cuobjdump not available")
+    assert "sm_100a" in sass
+    assert "UTMALDG" in sass
+    assert "VIMNMX3.U16x2" in sass or "VIMNMX3" in sass
+    assert "IDP.4A" in sass
+
+
+def test_reference_op_list_matches_the_reference(dip):
+    L = dip.lib()
+    from dip_benchmark_b200 import capi
+    arr = (capi.Op * 12)()
+    assert L.dip_reference_ops(arr, 12) == 12
+    prefixes = [L.dip_reference_op_prefix(i).decode() for i in range(12)]
+    assert prefixes == [p for p, _, _ in dip.REFERENCE_OPS]
+    assert L.dip_reference_op_description(4) == b"Erosion (3x3 Cross Kernel)"
+    assert L.dip_reference_ops(arr, 3) < 0
+
+
+def test_no_device_fails_loudly(dip):
+    n = C.c_int(-1)
+    rc = dip.lib().dip_device_count(C.byref(n))
+    if rc == 0 and n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(dip.DipError) as e:
+        dip.Context(0)
+    assert "no CPU fallback" in str(e.value)

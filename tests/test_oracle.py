@@ -1,0 +1,109 @@
+"""CPU: the oracle (oracle/dip_oracle.c) against the golden vectors generated from the
+reference's own cv2 calls (tests/golden/make_golden.py), and its own invariants."""
+import hashlib
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def digest(a):
+    b = np.ascontiguousarray(a).tobytes()
+    return {"sha256_16": hashlib.sha256(b).hexdigest()[:16], "crc32": f"{zlib.crc32(b):08x}"}
+
+
+def test_small_cases_match_reference_outputs(orc, golden_small):
+    keys = sorted({k.split("/")[0] for k in golden_small.files})
+    assert len(keys) == 36
+    for key in keys:
+        img = golden_small[f"{key}/input"]
+        for prefix, fn in orc.OPERATIONS:
+            want = golden_small[f"{key}/{prefix}"]
+            got = fn(img)
+            assert np.array_equal(got, want), f"{key} {prefix}: {(got != want).sum()} bytes differ"
+
+
+def test_generic_arguments_match_reference_outputs(orc, golden_generic):
+    g = golden_generic
+    img = g["input"]
+    for name in [k.split("/", 1)[1] for k in g.files if k.startswith("mask/")]:
+        assert np.array_equal(orc.erode(img, g[f"mask/{name}"]), g[f"erode/{name}"]), name
+        assert np.array_equal(orc.dilate(img, g[f"mask/{name}"]), g[f"dilate/{name}"]), name
+    for name in [k.split("/", 1)[1] for k in g.files if k.startswith("kernel/")]:
+        got = orc.filter2d(img, g[f"kernel/{name}"]).astype(int)
+        want = g[f"filter2d/{name}"].astype(int)
+        # dyadic kernels are exact; the non-dyadic box filter may differ by float summation order
+        tol = 1 if name == "box3" else 0
+        assert np.abs(got - want).max() <= tol, name
+    for key in [k for k in g.files if k.startswith("threshold/")]:
+        t, mv = (int(v) for v in key.split("/")[1].split("_"))
+        assert np.array_equal(orc.threshold(img, t, mv), g[key]), key
+
+
+def test_full_size_known_answers(orc, kat):
+    """hashes of every op's output on the full-size inputs."""
+    B = np.random.default_rng(0).integers(0, 256, (2336, 3504, 3), dtype=np.uint8)
+    assert digest(B) == {k: kat["inputs"]["B_rng0"][k] for k in ("sha256_16", "crc32")}
+    S = orc.synth(3504, 2336, 3, seed=0, frame=0)
+    assert digest(S)["sha256_16"] == kat["inputs"]["S_synth_seed0_frame0"]["sha256_16"]
+    for prefix, fn in orc.OPERATIONS:
+        assert digest(fn(B)) == kat["outputs"]["B_rng0"][prefix], prefix
+    # the synthetic generator's frame: only the two cheapest and the two rounding-critical ops
+    for prefix, fn in orc.OPERATIONS:
+        if prefix in ("grayscale", "erosion-cross", "convolution-gaussian-blur-3x3-separated", "gaussian-blur-3x3"):
+            assert digest(fn(S)) == kat["outputs"]["S_synth_seed0_frame0"][prefix], prefix
+
+
+def test_fundus_known_answers(orc, kat):
+    """The HRF fundus image (BASELINE.json config 0-2); decoded by cv2 or PIL, hash-gated."""
+    path = os.path.join(ROOT, "data", "fundus.jpg")
+    img = None
+    try:
+        import cv2
+        img = cv2.imread(path)
+    except Exception:  # noqa: BLE001
+        pass
+    if img is None or digest(img)["sha256_16"] != kat["inputs"]["A_fundus"]["sha256_16"]:
+        pytest.skip("JPEG decoder differs from the one that made the known answers")
+    for prefix, fn in orc.OPERATIONS:
+        assert digest(fn(img)) == kat["outputs"]["A_fundus"][prefix], prefix
+
+
+def test_grayscale_exhaustive_formula(orc):
+    """Y = (3735 B + 19235 G + 9798 R + 16384) >> 15 over a dense colour lattice + numpy restatement."""
+    v = np.arange(0, 256, 5, dtype=np.uint8)
+    b, g, r = np.meshgrid(v, v, v, indexing="ij")
+    img = np.stack([b.ravel(), g.ravel(), r.ravel()], axis=1).reshape(1, -1, 3)
+    y = ((img[..., 0].astype(np.uint32) * 3735 + img[..., 1].astype(np.uint32) * 19235 + img[..., 2].astype(np.uint32) * 9798 + 16384) >> 15).astype(np.uint8)
+    out = orc.grayscale(img)
+    assert np.array_equal(out, np.repeat(y[..., None], 3, axis=2))
+
+
+def test_invariants(orc):
+    rng = np.random.default_rng(7)
+    img = rng.integers(0, 256, (37, 29, 3), dtype=np.uint8)
+    assert np.array_equal(orc.invert(orc.invert(img)), img)
+    assert np.array_equal(orc.erode_separable(img), orc.erode(img, orc.SQUARE_MASK))
+    th = orc.threshold(img)
+    assert np.array_equal(orc.threshold(th), th)
+    flat = np.full((9, 11, 4), 77, np.uint8)
+    for k in (orc.BLUR_3X3, orc.BLUR_5X5):
+        assert np.array_equal(orc.filter2d(flat, k), flat)
+    assert np.array_equal(orc.gaussian_blur3x3(flat), flat)
+    # the full and the separable Gaussian differ only by double rounding: at most 1 LSB
+    d = orc.filter2d(img, orc.BLUR_5X5).astype(int) - orc.filter2d_separable(img, orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1).astype(int)
+    assert np.abs(d).max() <= 1
+    assert orc.checksum(img) != orc.checksum(orc.invert(img))
+
+
+def test_numpy_restatement_of_packed_rounding():
+    """The identity the CUDA kernels use: RNE(S / 2^s) = (R + ((R >> s) & 1)) >> s with R = S + 2^(s-1) - 1."""
+    for s, smax in ((2, 1020), (4, 4080), (8, 65280)):
+        S = np.arange(0, smax + 1, dtype=np.int64)
+        R = S + (1 << (s - 1)) - 1
+        got = (R + ((R >> s) & 1)) >> s
+        want = np.rint(S / float(1 << s)).astype(np.int64)  # numpy rint is round-half-even
+        assert np.array_equal(got, want), s

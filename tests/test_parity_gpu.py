@@ -1,0 +1,249 @@
+"""GPU: every operation of the C-ABI against the CPU oracle (bit-exact), the golden vectors
+generated from the reference's cv2 calls, and size-independent properties at full size.
+
+All calls go through libdip_b200.so (ctypes over include/dip.h)."""
+import hashlib
+import os
+import zlib
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SHAPES = [(1, 1), (1, 2), (2, 1), (2, 2), (1, 9), (9, 1), (3, 3), (5, 7), (7, 5), (16, 16), (33, 47), (64, 130),
+          (66, 171), (70, 512), (129, 683), (200, 1031)]
+
+
+def digest(a):
+    b = np.ascontiguousarray(a).tobytes()
+    return {"sha256_16": hashlib.sha256(b).hexdigest()[:16], "crc32": f"{zlib.crc32(b):08x}"}
+
+
+def run_op(ctx, name, args, img):
+    """img: HxWxC or NxHxWxC ndarray -> result of the same shape, through the C-ABI."""
+    src = ctx.from_array(img)
+    dst = ctx.image_like(src)
+    getattr(ctx, name)(src, dst, *args)
+    out = dst.download().reshape(img.shape)
+    src.close(); dst.close()
+    return out
+
+
+def rand_img(rng, h, w, c):
+    img = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+    if h * w >= 9:  # flat / extreme regions exercise rounding ties and saturation
+        img[: h // 2, : w // 2] = (img[: h // 2, : w // 2] // 64) * 85
+    return img
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_all_reference_ops_match_oracle(ctx, dip, orc, c):
+    rng = np.random.default_rng(100 + c)
+    for (h, w) in SHAPES:
+        img = rand_img(rng, h, w, c)
+        for (prefix, name, args), (oprefix, ofn) in zip(dip.REFERENCE_OPS, orc.OPERATIONS):
+            assert prefix == oprefix
+            got = run_op(ctx, name, args, img)
+            want = ofn(img)
+            assert np.array_equal(got, want), f"{prefix} {h}x{w}x{c}: {(got != want).sum()} bytes differ"
+
+
+def test_golden_small_cases(ctx, dip, golden_small):
+    """Outputs of the reference's own cv2 calls, committed under tests/golden/."""
+    keys = sorted({k.split("/")[0] for k in golden_small.files})
+    for key in keys:
+        img = golden_small[f"{key}/input"]
+        for prefix, name, args in dip.REFERENCE_OPS:
+            got = run_op(ctx, name, args, img)
+            assert np.array_equal(got, golden_small[f"{key}/{prefix}"]), f"{key} {prefix}"
+
+
+def test_golden_generic_arguments(ctx, golden_generic):
+    g = golden_generic
+    img = g["input"]
+    for name in [k.split("/", 1)[1] for k in g.files if k.startswith("mask/")]:
+        assert np.array_equal(run_op(ctx, "erode", (g[f"mask/{name}"],), img), g[f"erode/{name}"]), name
+        assert np.array_equal(run_op(ctx, "dilate", (g[f"mask/{name}"],), img), g[f"dilate/{name}"]), name
+    for name in [k.split("/", 1)[1] for k in g.files if k.startswith("kernel/")]:
+        got = run_op(ctx, "convolve", (g[f"kernel/{name}"],), img).astype(int)
+        want = g[f"filter2d/{name}"].astype(int)
+        tol = 1 if name == "box3" else 0  # north_star: +-1 LSB where the reference rounds float sums
+        assert np.abs(got - want).max() <= tol, name
+    for key in [k for k in g.files if k.startswith("threshold/")]:
+        t, mv = (int(v) for v in key.split("/")[1].split("_"))
+        assert np.array_equal(run_op(ctx, "threshold", (t, mv), img), g[key]), key
+
+
+def test_full_size_known_answers(ctx, dip, kat):
+    """BASELINE.json configs 1-3 shape (3504x2336 RGB): SURVEY.md 8.1 hashes for input B."""
+    B = np.random.default_rng(0).integers(0, 256, (2336, 3504, 3), dtype=np.uint8)
+    src = ctx.from_array(B)
+    dst = ctx.image_like(src)
+    for prefix, name, args in dip.REFERENCE_OPS:
+        getattr(ctx, name)(src, dst, *args)
+        assert digest(dst.download()) == kat["outputs"]["B_rng0"][prefix], prefix
+    src.close(); dst.close()
+
+
+def test_fundus_known_answers(ctx, dip, kat):
+    path = os.path.join(ROOT, "data", "fundus.jpg")
+    try:
+        import cv2
+        img = cv2.imread(path)
+    except Exception:  # noqa: BLE001
+        img = None
+    if img is None or digest(img)["sha256_16"] != kat["inputs"]["A_fundus"]["sha256_16"]:
+        pytest.skip("JPEG decoder differs from the one that made the known answers")
+    src = ctx.from_array(img)
+    dst = ctx.image_like(src)
+    for prefix, name, args in dip.REFERENCE_OPS:
+        getattr(ctx, name)(src, dst, *args)
+        assert digest(dst.download()) == kat["outputs"]["A_fundus"][prefix], prefix
+    src.close(); dst.close()
+
+
+def test_synth_and_checksum_match_oracle(ctx, orc, kat):
+    img = ctx.image(3504, 2336, 3, frames=3)
+    img.synth_fill(seed=0, first_frame=0)
+    host = img.download()
+    assert digest(host[0])["sha256_16"] == kat["inputs"]["S_synth_seed0_frame0"]["sha256_16"]
+    for f in range(3):
+        assert np.array_equal(host[f], orc.synth(3504, 2336, 3, seed=0, frame=f))
+    assert img.checksum() == [orc.checksum(host[f]) for f in range(3)]
+    img.close()
+    odd = ctx.image(37, 11, 3, frames=2).synth_fill(seed=5, first_frame=7)
+    h = odd.download()
+    assert np.array_equal(h[1], orc.synth(37, 11, 3, seed=5, frame=8))
+    assert odd.checksum() == [orc.checksum(h[0]), orc.checksum(h[1])]
+    odd.close()
+
+
+def test_batch_is_one_launch_and_matches_per_frame(ctx, dip, orc):
+    rng = np.random.default_rng(5)
+    stack = rng.integers(0, 256, (5, 70, 173, 3), dtype=np.uint8)
+    src = ctx.from_array(stack)
+    dst = ctx.image_like(src)
+    for (prefix, name, args), (_, ofn) in zip(dip.REFERENCE_OPS, orc.OPERATIONS):
+        before = ctx.launch_count()
+        getattr(ctx, name)(src, dst, *args)
+        assert ctx.launch_count() - before == 1, prefix
+        got = dst.download()
+        for f in range(stack.shape[0]):
+            assert np.array_equal(got[f], ofn(stack[f])), f"{prefix} frame {f}"
+    # views address single frames of the stack
+    v = src.view(3, 2)
+    o = ctx.image(173, 70, 3, frames=2)
+    ctx.invert(v, o)
+    assert np.array_equal(o.download(), 255 - stack[3:5])
+    src.close(); dst.close(); o.close()
+
+
+def test_full_size_batch_properties(ctx, dip, orc):
+    """BASELINE.json config 4 shape, device-generated frames: checksum-of-checksums and identities."""
+    n = 6
+    src = ctx.image(3504, 2336, 3, frames=n).synth_fill(seed=1, first_frame=40)
+    a = ctx.image_like(src)
+    b = ctx.image_like(src)
+    cs_src = src.checksum()
+    ctx.invert(src, a); ctx.invert(a, b)
+    assert b.checksum() == cs_src                               # involution
+    ctx.erode(src, a, dip.ops.SQUARE_MASK); ctx.erode_separable(src, b, 3, 3)
+    assert a.checksum() == b.checksum()                         # separable == square erosion
+    ctx.threshold(src, a, 127, 255); ctx.threshold(a, b, 127, 255)
+    assert a.checksum() == b.checksum()                         # idempotent
+    # spot-check two frames of every op against the oracle through checksums
+    for (prefix, name, args), (_, ofn) in zip(dip.REFERENCE_OPS, orc.OPERATIONS):
+        getattr(ctx, name)(src, a, *args)
+        cs = a.checksum()
+        for f in (0, n - 1):
+            want = orc.checksum(ofn(orc.synth(3504, 2336, 3, seed=1, frame=40 + f)))
+            assert cs[f] == want, f"{prefix} frame {f}"
+    for im in (src, a, b):
+        im.close()
+
+
+def test_linearity_and_constant_images(ctx, dip):
+    flat = np.full((50, 77, 3), 131, np.uint8)
+    for prefix, name, args in dip.REFERENCE_OPS:
+        if prefix.startswith("convolution") or prefix.startswith("gaussian") or prefix.startswith("erosion") or prefix == "copy":
+            assert np.array_equal(run_op(ctx, name, args, flat), flat), prefix
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 128, (40, 90, 4), dtype=np.uint8)
+    # an integer-weight Gaussian of 2x the image is within rounding of 2x the Gaussian
+    g1 = run_op(ctx, "convolve", (dip.ops.BLUR_5X5,), img).astype(int)
+    g2 = run_op(ctx, "convolve", (dip.ops.BLUR_5X5,), (img * 2).astype(np.uint8)).astype(int)
+    assert np.abs(g2 - 2 * g1).max() <= 1
+
+
+def test_transfers_pinned_pageable_and_pitch(ctx, dip):
+    rng = np.random.default_rng(2)
+    for shape in [(2336, 3504, 3), (33, 47, 3), (1, 1, 1), (300, 1001, 4)]:
+        a = rng.integers(0, 256, shape, dtype=np.uint8)
+        img = ctx.from_array(a)                 # pageable upload through the staging slots
+        assert np.array_equal(img.download(), a)  # pageable download
+        pin = ctx.pinned_empty(shape)
+        pin[...] = a[::-1]
+        img.upload(pin)                         # pinned upload, single async copy
+        out = ctx.pinned_empty(shape)
+        img.download(out)
+        assert np.array_equal(out, a[::-1])
+        dip.ops.free_pinned(pin); dip.ops.free_pinned(out)
+        img.close()
+
+
+def test_apply_rows_bands_reproduce_whole_image(ctx, dip, orc):
+    """Row bands with recomputed overlap (mosaic configuration) == whole image, on one GPU."""
+    rng = np.random.default_rng(4)
+    mosaic = rng.integers(0, 256, (301, 700, 1), dtype=np.uint8)
+    want = orc.erode(orc.filter2d(mosaic, orc.BLUR_5X5), orc.SQUARE_MASK)
+    ops = {p: op for _, p, op in ctx.reference_ops()}
+    chain = [ops["convolution-gaussian-blur-5x5"], ops["erosion-square"]]
+    sh = dip.shard
+    for world in (1, 2, 4):
+        out = np.zeros_like(mosaic)
+        for rank in range(world):
+            b = sh.mosaic_band(mosaic.shape[0], world, rank, 3)
+            buf = np.zeros((b.buffer_rows,) + mosaic.shape[1:], np.uint8)
+            lo = b.row0 - (3 if b.has_above else 0)
+            hi = b.row0 + b.rows + (3 if b.has_below else 0)
+            buf[b.own0 - (b.row0 - lo): b.own0 - (b.row0 - lo) + (hi - lo)] = mosaic[lo:hi]
+            bufs = [ctx.from_array(buf), ctx.image(700, b.buffer_rows, 1), ctx.image(700, b.buffer_rows, 1)]
+            for k, st in enumerate(sh.chain_row_plan(b, [2, 1])):
+                ctx.apply_rows(chain[k], bufs[k], st["valid_row0"], st["valid_rows"], st["out_row0"], st["out_rows"],
+                               bufs[k + 1], st["dst_row0"])
+            res = bufs[2].download()
+            out[b.row0: b.row0 + b.rows] = res[b.own0: b.own0 + b.rows]
+            for im in bufs:
+                im.close()
+        assert np.array_equal(out, want), world
+
+
+def test_run_ops_host_pipeline(ctx, dip, orc):
+    rng = np.random.default_rng(6)
+    batch = rng.integers(0, 256, (7, 120, 333, 3), dtype=np.uint8)
+    ops = [op for _, _, op in ctx.reference_ops()]
+    outs = [np.empty_like(batch) for _ in ops]
+    ctx.run_ops_host(batch, ops, outs, chunk_frames=3)
+    for o, (prefix, ofn) in zip(outs, orc.OPERATIONS):
+        for f in range(batch.shape[0]):
+            assert np.array_equal(o[f], ofn(batch[f])), f"{prefix} frame {f}"
+
+
+def test_error_behaviour(ctx, dip):
+    a = ctx.image(32, 16, 3)
+    b = ctx.image(33, 16, 3)
+    with pytest.raises(dip.DipError) as e:
+        ctx.invert(a, b)
+    assert e.value.code == -2
+    with pytest.raises(dip.DipError) as e:
+        ctx.erode(a, a, dip.ops.SQUARE_MASK)     # in-place stencil
+    assert e.value.code == -2
+    with pytest.raises(dip.DipError):
+        ctx.image(10, 10, 2)                      # channels
+    with pytest.raises(dip.DipError):
+        ctx.erode(a, ctx.image(32, 16, 3), np.zeros((3, 3), np.uint8))  # empty mask
+    ctx.invert(a, a)                              # in-place point op is allowed
+    ctx.sync()
