@@ -111,6 +111,11 @@ def lib() -> C.CDLL:
         "dip_reference_op_prefix": ([i], C.c_char_p),
         "dip_reference_op_description": ([i], C.c_char_p),
         "dip_run_ops_host": ([vp, vp, i, i, i, i, P(Op), i, P(vp), i], i),
+        "dip_pipeline_create": ([vp, i, i, i, i, P(Op), i, P(vp)], i),
+        "dip_pipeline_run": ([vp, vp, i, i, P(vp), i], i),
+        "dip_pipeline_destroy": ([vp], i),
+        "dip_mark": ([vp, i], i),
+        "dip_elapsed": ([vp, i, i, P(C.c_float)], i),
         "dip_timer_start": ([vp], i),
         "dip_timer_stop": ([vp, P(C.c_float)], i),
         "dip_launch_count": ([vp, P(C.c_uint64)], i),

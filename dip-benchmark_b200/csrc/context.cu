@@ -221,6 +221,7 @@ int dip_shutdown(dip_ctx* ctx) {
         if (ctx->stage_up_free[i]) cudaEventDestroy(ctx->stage_up_free[i]);
         if (ctx->stage_dn_done[i]) cudaEventDestroy(ctx->stage_dn_done[i]);
     }
+    for (cudaEvent_t e : ctx->marks) cudaEventDestroy(e);
     if (ctx->flush_buf) cudaFree(ctx->flush_buf);
     if (ctx->d_checksums) cudaFree(ctx->d_checksums);
     cudaEventDestroy(ctx->ev_compute);
@@ -411,6 +412,79 @@ static int copy_2d(dip_ctx* ctx, cudaStream_t s, void* dst, size_t dpitch, size_
     return DIP_OK;
 }
 
+}  // extern "C"
+
+namespace dip {
+
+int enqueue_upload(dip_ctx* ctx, const ImgView& v, const uint8_t* host, size_t host_pitch) {
+    const size_t rowb = (size_t)v.rowbytes;
+    if (is_pinned(host))
+        return copy_2d(ctx, ctx->upload, v.base, v.pitch, v.frame_stride, host, host_pitch, host_pitch * (size_t)v.height, rowb,
+                       v.height, v.frames, cudaMemcpyHostToDevice);
+    // pageable: stage row slices through two pinned slots, copy of slice k overlaps staging of k+1
+    const int rows_per_slice = (int)std::max<size_t>(1, ctx->stage_bytes / rowb);
+    int slot = 0;
+    for (int f = 0; f < v.frames; ++f) {
+        for (int y = 0; y < v.height; y += rows_per_slice) {
+            const int rows = std::min(rows_per_slice, v.height - y);
+            DIP_CUDA(ctx, cudaEventSynchronize(ctx->stage_up_free[slot]));
+            uint8_t* st = ctx->stage_up[slot];
+            const uint8_t* hsrc = host + host_pitch * ((size_t)f * v.height + y);
+            if (host_pitch == rowb) memcpy(st, hsrc, rowb * rows);
+            else for (int r = 0; r < rows; ++r) memcpy(st + rowb * r, hsrc + host_pitch * r, rowb);
+            DIP_CUDA(ctx, cudaMemcpy2DAsync(v.base + v.frame_stride * (size_t)f + v.pitch * (size_t)y, v.pitch, st, rowb, rowb,
+                                            rows, cudaMemcpyHostToDevice, ctx->upload));
+            DIP_CUDA(ctx, cudaEventRecord(ctx->stage_up_free[slot], ctx->upload));
+            slot ^= 1;
+        }
+    }
+    return DIP_OK;
+}
+
+int enqueue_download(dip_ctx* ctx, const ImgView& v, uint8_t* host, size_t host_pitch, bool* completed) {
+    const size_t rowb = (size_t)v.rowbytes;
+    if (is_pinned(host)) {
+        *completed = false;
+        return copy_2d(ctx, ctx->download, host, host_pitch, host_pitch * (size_t)v.height, v.base, v.pitch, v.frame_stride, rowb,
+                       v.height, v.frames, cudaMemcpyDeviceToHost);
+    }
+    // pageable destination: D2H into pinned slots, drain slot k while slot k+1 is in flight.
+    // The host memcpy needs the data, so this path completes before returning.
+    *completed = true;
+    const int rows_per_slice = (int)std::max<size_t>(1, ctx->stage_bytes / rowb);
+    struct Pending { uint8_t* hdst; int rows; bool live; } pend[dip_ctx::kSlots] = {};
+    int slot = 0;
+    auto drain = [&](int s) -> int {
+        if (!pend[s].live) return DIP_OK;
+        DIP_CUDA(ctx, cudaEventSynchronize(ctx->stage_dn_done[s]));
+        if (host_pitch == rowb) memcpy(pend[s].hdst, ctx->stage_dn[s], rowb * pend[s].rows);
+        else for (int r = 0; r < pend[s].rows; ++r) memcpy(pend[s].hdst + host_pitch * r, ctx->stage_dn[s] + rowb * r, rowb);
+        pend[s].live = false;
+        return DIP_OK;
+    };
+    for (int f = 0; f < v.frames; ++f) {
+        for (int y = 0; y < v.height; y += rows_per_slice) {
+            const int rows = std::min(rows_per_slice, v.height - y);
+            int rc = drain(slot);
+            if (rc != DIP_OK) return rc;
+            DIP_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_dn[slot], rowb, v.base + v.frame_stride * (size_t)f + v.pitch * (size_t)y,
+                                            v.pitch, rowb, rows, cudaMemcpyDeviceToHost, ctx->download));
+            DIP_CUDA(ctx, cudaEventRecord(ctx->stage_dn_done[slot], ctx->download));
+            pend[slot] = Pending{host + host_pitch * ((size_t)f * v.height + y), rows, true};
+            slot ^= 1;
+        }
+    }
+    for (int s = 0; s < dip_ctx::kSlots; ++s) {
+        int rc = drain(s);
+        if (rc != DIP_OK) return rc;
+    }
+    return DIP_OK;
+}
+
+}  // namespace dip
+
+extern "C" {
+
 int dip_upload(dip_ctx* ctx, dip_image* dst_view, const uint8_t* host, size_t host_pitch) {
     if (!ctx || !dst_view || !host) return fail(ctx, DIP_ERR_ARG, "null argument");
     DIP_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -423,29 +497,8 @@ int dip_upload(dip_ctx* ctx, dip_image* dst_view, const uint8_t* host, size_t ho
     DIP_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->compute));
     DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->upload, ctx->ev_compute, 0));
     if (dst->copy_pending) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->upload, dst->copy_done, 0));
-    if (is_pinned(host)) {
-        int rc = copy_2d(ctx, ctx->upload, v.base, v.pitch, v.frame_stride, host, host_pitch, host_pitch * (size_t)v.height,
-                         rowb, v.height, v.frames, cudaMemcpyHostToDevice);
-        if (rc != DIP_OK) return rc;
-    } else {
-        // pageable: stage row slices through two pinned slots, copy of slice k overlaps staging of k+1
-        const int rows_per_slice = (int)std::max<size_t>(1, ctx->stage_bytes / rowb);
-        int slot = 0;
-        for (int f = 0; f < v.frames; ++f) {
-            for (int y = 0; y < v.height; y += rows_per_slice) {
-                const int rows = std::min(rows_per_slice, v.height - y);
-                DIP_CUDA(ctx, cudaEventSynchronize(ctx->stage_up_free[slot]));
-                uint8_t* st = ctx->stage_up[slot];
-                const uint8_t* hsrc = host + host_pitch * ((size_t)f * v.height + y);
-                if (host_pitch == rowb) memcpy(st, hsrc, rowb * rows);
-                else for (int r = 0; r < rows; ++r) memcpy(st + rowb * r, hsrc + host_pitch * r, rowb);
-                DIP_CUDA(ctx, cudaMemcpy2DAsync(v.base + v.frame_stride * (size_t)f + v.pitch * (size_t)y, v.pitch, st,
-                                                rowb, rowb, rows, cudaMemcpyHostToDevice, ctx->upload));
-                DIP_CUDA(ctx, cudaEventRecord(ctx->stage_up_free[slot], ctx->upload));
-                slot ^= 1;
-            }
-        }
-    }
+    int rc = enqueue_upload(ctx, v, host, host_pitch);
+    if (rc != DIP_OK) return rc;
     DIP_CUDA(ctx, cudaEventRecord(dst->copy_done, ctx->upload));
     dst->copy_pending = true;
     return DIP_OK;
@@ -462,42 +515,12 @@ int dip_download(dip_ctx* ctx, const dip_image* src_c, uint8_t* host, size_t hos
     DIP_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->compute));
     DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->download, ctx->ev_compute, 0));
     if (src->copy_pending) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->download, src->copy_done, 0));
-    if (is_pinned(host)) {
-        int rc = copy_2d(ctx, ctx->download, host, host_pitch, host_pitch * (size_t)v.height, v.base, v.pitch, v.frame_stride,
-                         rowb, v.height, v.frames, cudaMemcpyDeviceToHost);
-        if (rc != DIP_OK) return rc;
+    bool completed = false;
+    int rc = enqueue_download(ctx, v, host, host_pitch, &completed);
+    if (rc != DIP_OK) return rc;
+    if (!completed) {
         DIP_CUDA(ctx, cudaEventRecord(src->copy_done, ctx->download));
         src->copy_pending = true;
-    } else {
-        // pageable destination: D2H into pinned slots, drain slot k while slot k+1 is in flight.
-        // The host memcpy needs the data, so this path completes before returning.
-        const int rows_per_slice = (int)std::max<size_t>(1, ctx->stage_bytes / rowb);
-        struct Pending { uint8_t* hdst; int rows; bool live; } pend[dip_ctx::kSlots] = {};
-        int slot = 0;
-        auto drain = [&](int s) -> int {
-            if (!pend[s].live) return DIP_OK;
-            DIP_CUDA(ctx, cudaEventSynchronize(ctx->stage_dn_done[s]));
-            if (host_pitch == rowb) memcpy(pend[s].hdst, ctx->stage_dn[s], rowb * pend[s].rows);
-            else for (int r = 0; r < pend[s].rows; ++r) memcpy(pend[s].hdst + host_pitch * r, ctx->stage_dn[s] + rowb * r, rowb);
-            pend[s].live = false;
-            return DIP_OK;
-        };
-        for (int f = 0; f < v.frames; ++f) {
-            for (int y = 0; y < v.height; y += rows_per_slice) {
-                const int rows = std::min(rows_per_slice, v.height - y);
-                int rc = drain(slot);
-                if (rc != DIP_OK) return rc;
-                DIP_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_dn[slot], rowb, v.base + v.frame_stride * (size_t)f + v.pitch * (size_t)y,
-                                                v.pitch, rowb, rows, cudaMemcpyDeviceToHost, ctx->download));
-                DIP_CUDA(ctx, cudaEventRecord(ctx->stage_dn_done[slot], ctx->download));
-                pend[slot] = Pending{host + host_pitch * ((size_t)f * v.height + y), rows, true};
-                slot ^= 1;
-            }
-        }
-        for (int s = 0; s < dip_ctx::kSlots; ++s) {
-            int rc = drain(s);
-            if (rc != DIP_OK) return rc;
-        }
     }
     return DIP_OK;
 }
@@ -514,6 +537,25 @@ int dip_timer_stop(dip_ctx* ctx, float* ms) {
     DIP_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->compute));
     DIP_CUDA(ctx, cudaEventSynchronize(ctx->t1));
     DIP_CUDA(ctx, cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
+    return DIP_OK;
+}
+
+int dip_mark(dip_ctx* ctx, int slot) {
+    if (!ctx || slot < 0 || slot > (1 << 20)) return fail(ctx, DIP_ERR_ARG, "bad marker slot");
+    while ((int)ctx->marks.size() <= slot) {
+        cudaEvent_t e = nullptr;
+        DIP_CUDA(ctx, cudaEventCreate(&e));
+        ctx->marks.push_back(e);
+    }
+    DIP_CUDA(ctx, cudaEventRecord(ctx->marks[slot], ctx->compute));
+    return DIP_OK;
+}
+
+int dip_elapsed(dip_ctx* ctx, int a, int b, float* ms) {
+    if (!ctx || !ms || a < 0 || b < 0 || a >= (int)ctx->marks.size() || b >= (int)ctx->marks.size())
+        return fail(ctx, DIP_ERR_ARG, "marker slot not recorded");
+    DIP_CUDA(ctx, cudaEventSynchronize(ctx->marks[b]));
+    DIP_CUDA(ctx, cudaEventElapsedTime(ms, ctx->marks[a], ctx->marks[b]));
     return DIP_OK;
 }
 

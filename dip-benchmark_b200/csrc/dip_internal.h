@@ -70,6 +70,7 @@ struct dip_ctx {
     size_t flush_bytes = 0;
     uint64_t* d_checksums = nullptr;
     int d_checksums_cap = 0;
+    std::vector<cudaEvent_t> marks;
     std::string last_error;
 };
 
@@ -95,6 +96,11 @@ int fail_cuda(const dip_ctx* ctx, cudaError_t e, const char* what, const char* f
 // Make the compute stream wait for outstanding copies on the operands, and set the device.
 int begin_op(dip_ctx* ctx, const dip_image* src, dip_image* dst);
 int check_pair(dip_ctx* ctx, const dip_image* src, const dip_image* dst, bool allow_inplace);
+
+// Raw transfers on the ctx's copy streams without any cross-stream ordering (callers order
+// them with their own events).  Pageable host memory goes through the pinned staging slots.
+int enqueue_upload(dip_ctx* ctx, const ImgView& v, const uint8_t* host, size_t host_pitch);
+int enqueue_download(dip_ctx* ctx, const ImgView& v, uint8_t* host, size_t host_pitch, bool* completed);
 
 // ---- kernels' host launchers (point_ops.cu) -----------------------------------------
 enum PointOp { kCopy = 0, kInvert = 1, kThreshold = 2 };

@@ -9,6 +9,22 @@
 
 using namespace dip;
 
+// Chunked three-stream pipeline: while chunk k's kernels run, chunk k+1 uploads and chunk k-1's
+// results download.  Two input stacks and two sets of output stacks rotate; ordering between the
+// streams is carried by per-slot events owned by the pipeline (not by the per-image tracking of
+// dip_upload / dip_download, which would serialise an upload behind all enqueued kernels).
+struct dip_pipeline {
+    dip_ctx* ctx = nullptr;
+    int w = 0, h = 0, c = 0, chunk = 0, n_ops = 0;
+    std::vector<dip_op> ops;
+    dip_image* in[2] = {nullptr, nullptr};
+    std::vector<dip_image*> out;              // [slot][op]
+    cudaEvent_t in_ready[2] = {nullptr, nullptr};   // upload of the slot finished
+    cudaEvent_t in_free[2] = {nullptr, nullptr};    // last kernel reading the slot finished
+    std::vector<cudaEvent_t> out_ready;       // [slot][op] kernel finished
+    std::vector<cudaEvent_t> out_free;        // [slot][op] download finished
+};
+
 namespace {
 
 // masks and kernels of opencv/benchmark.py:46-72
@@ -93,47 +109,19 @@ int dip_apply(dip_ctx* ctx, const dip_op* op, const dip_image* src, dip_image* d
     return fail(ctx, DIP_ERR_ARG, "unknown operation kind %d", op->kind);
 }
 
-// Chunked three-stream pipeline: while chunk k's kernels run, chunk k+1 uploads and chunk
-// k-1's results download.  Two input stacks and two sets of output stacks rotate.
+// One-shot form of the pipeline below.
 int dip_run_ops_host(dip_ctx* ctx, const uint8_t* host_in, int w, int h, int c, int frames, const dip_op* ops, int n_ops,
                      uint8_t* const* host_out, int chunk_frames) {
     if (!ctx || !host_in || !ops || !host_out || n_ops < 1 || frames < 1) return fail(ctx, DIP_ERR_ARG, "bad argument");
     if (chunk_frames < 1) chunk_frames = 4;
     chunk_frames = std::min(chunk_frames, frames);
-    const size_t frame_bytes = (size_t)w * c * h;
-    dip_image* in[2] = {nullptr, nullptr};
-    std::vector<dip_image*> out(2 * (size_t)n_ops, nullptr);
-    int rc = DIP_OK;
-    auto cleanup = [&]() {
-        dip_sync(ctx);
-        for (dip_image* im : in) dip_image_destroy(im);
-        for (dip_image* im : out) dip_image_destroy(im);
-    };
-    for (int s = 0; s < 2 && rc == DIP_OK; ++s) {
-        rc = dip_image_create_batch(ctx, w, h, c, chunk_frames, &in[s]);
-        for (int o = 0; o < n_ops && rc == DIP_OK; ++o) rc = dip_image_create_batch(ctx, w, h, c, chunk_frames, &out[(size_t)s * n_ops + o]);
-    }
-    if (rc != DIP_OK) { cleanup(); return rc; }
-    int slot = 0;
-    for (int f0 = 0; f0 < frames && rc == DIP_OK; f0 += chunk_frames, slot ^= 1) {
-        const int n = std::min(chunk_frames, frames - f0);
-        dip_image *iv = nullptr;
-        rc = dip_image_view(ctx, in[slot], 0, n, &iv);
-        if (rc != DIP_OK) break;
-        rc = dip_upload(ctx, iv, host_in + frame_bytes * (size_t)f0, 0);
-        for (int o = 0; o < n_ops && rc == DIP_OK; ++o) {
-            dip_image* ov = nullptr;
-            rc = dip_image_view(ctx, out[(size_t)slot * n_ops + o], 0, n, &ov);
-            if (rc != DIP_OK) break;
-            rc = dip_apply(ctx, &ops[o], iv, ov);
-            if (rc == DIP_OK) rc = dip_download(ctx, ov, host_out[o] + frame_bytes * (size_t)f0, 0);
-            dip_image_destroy(ov);
-        }
-        dip_image_destroy(iv);
-    }
-    cleanup();
+    dip_pipeline* p = nullptr;
+    int rc = dip_pipeline_create(ctx, w, h, c, chunk_frames, ops, n_ops, &p);
     if (rc != DIP_OK) return rc;
-    return DIP_OK;
+    const int ring = (frames + chunk_frames - 1) / chunk_frames * chunk_frames;  // no wrap: plain arrays
+    rc = dip_pipeline_run(p, host_in, ring, frames, host_out, ring);
+    dip_pipeline_destroy(p);
+    return rc;
 }
 
 }  // extern "C"
@@ -169,3 +157,93 @@ extern "C" int dip_apply_rows(dip_ctx* ctx, const dip_op* op, const dip_image* s
     dip_image_destroy(dv);
     return rc;
 }
+
+extern "C" {
+
+int dip_pipeline_create(dip_ctx* ctx, int w, int h, int c, int chunk_frames, const dip_op* ops, int n_ops, dip_pipeline** out) {
+    if (!ctx || !ops || !out || n_ops < 1 || chunk_frames < 1) return fail(ctx, DIP_ERR_ARG, "bad argument");
+    *out = nullptr;
+    dip_pipeline* p = new (std::nothrow) dip_pipeline();
+    if (!p) return fail(ctx, DIP_ERR_NOMEM, "out of host memory");
+    p->ctx = ctx; p->w = w; p->h = h; p->c = c; p->chunk = chunk_frames; p->n_ops = n_ops;
+    p->ops.assign(ops, ops + n_ops);
+    p->out.assign(2 * (size_t)n_ops, nullptr);
+    p->out_ready.assign(2 * (size_t)n_ops, nullptr);
+    p->out_free.assign(2 * (size_t)n_ops, nullptr);
+    int rc = DIP_OK;
+    cudaSetDevice(ctx->device);
+    auto mk = [&](cudaEvent_t* e) { if (rc == DIP_OK && cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) rc = fail(ctx, DIP_ERR_CUDA, "cudaEventCreate failed"); };
+    for (int s = 0; s < 2 && rc == DIP_OK; ++s) {
+        rc = dip_image_create_batch(ctx, w, h, c, chunk_frames, &p->in[s]);
+        mk(&p->in_ready[s]); mk(&p->in_free[s]);
+        for (int o = 0; o < n_ops && rc == DIP_OK; ++o) {
+            rc = dip_image_create_batch(ctx, w, h, c, chunk_frames, &p->out[(size_t)s * n_ops + o]);
+            mk(&p->out_ready[(size_t)s * n_ops + o]); mk(&p->out_free[(size_t)s * n_ops + o]);
+        }
+    }
+    if (rc != DIP_OK) { dip_pipeline_destroy(p); return rc; }
+    *out = p;
+    return DIP_OK;
+}
+
+int dip_pipeline_destroy(dip_pipeline* p) {
+    if (!p) return DIP_OK;
+    dip_sync(p->ctx);
+    for (int s = 0; s < 2; ++s) {
+        dip_image_destroy(p->in[s]);
+        if (p->in_ready[s]) cudaEventDestroy(p->in_ready[s]);
+        if (p->in_free[s]) cudaEventDestroy(p->in_free[s]);
+    }
+    for (dip_image* im : p->out) dip_image_destroy(im);
+    for (cudaEvent_t e : p->out_ready) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : p->out_free) if (e) cudaEventDestroy(e);
+    delete p;
+    return DIP_OK;
+}
+
+int dip_pipeline_run(dip_pipeline* p, const uint8_t* host_in, int in_ring, int frames, uint8_t* const* host_out, int out_ring) {
+    if (!p || !host_in || !host_out || frames < 1) return fail(p ? p->ctx : nullptr, DIP_ERR_ARG, "bad argument");
+    dip_ctx* ctx = p->ctx;
+    if (in_ring < p->chunk || out_ring < p->chunk || in_ring % p->chunk || out_ring % p->chunk)
+        return fail(ctx, DIP_ERR_ARG, "host ring sizes must be positive multiples of chunk_frames (%d)", p->chunk);
+    DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t frame_bytes = (size_t)p->w * p->c * p->h;
+    int rc = DIP_OK;
+    int slot = 0;
+    bool used[2] = {false, false};
+    for (int f0 = 0; f0 < frames && rc == DIP_OK; f0 += p->chunk, slot ^= 1) {
+        const int n = std::min(p->chunk, frames - f0);
+        dip_image* iv = nullptr;
+        if ((rc = dip_image_view(ctx, p->in[slot], 0, n, &iv)) != DIP_OK) break;
+        // H2D: wait until the kernels of two chunks ago released this input slot
+        if (used[slot]) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->upload, p->in_free[slot], 0));
+        rc = enqueue_upload(ctx, iv->v, host_in + frame_bytes * (size_t)(f0 % in_ring), frame_bytes / p->h);
+        if (rc == DIP_OK) {
+            DIP_CUDA(ctx, cudaEventRecord(p->in_ready[slot], ctx->upload));
+            DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, p->in_ready[slot], 0));
+        }
+        for (int o = 0; o < p->n_ops && rc == DIP_OK; ++o) {
+            const size_t idx = (size_t)slot * p->n_ops + o;
+            dip_image* ov = nullptr;
+            if ((rc = dip_image_view(ctx, p->out[idx], 0, n, &ov)) != DIP_OK) break;
+            // the kernel may overwrite this output slot only after its previous download finished
+            if (used[slot]) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, p->out_free[idx], 0));
+            rc = dip_apply(ctx, &p->ops[o], iv, ov);
+            if (rc == DIP_OK) {
+                DIP_CUDA(ctx, cudaEventRecord(p->out_ready[idx], ctx->compute));
+                DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->download, p->out_ready[idx], 0));
+                bool completed = false;
+                rc = enqueue_download(ctx, ov->v, host_out[o] + frame_bytes * (size_t)(f0 % out_ring), frame_bytes / p->h, &completed);
+                if (rc == DIP_OK) DIP_CUDA(ctx, cudaEventRecord(p->out_free[idx], ctx->download));
+            }
+            dip_image_destroy(ov);
+        }
+        if (rc == DIP_OK) DIP_CUDA(ctx, cudaEventRecord(p->in_free[slot], ctx->compute));
+        used[slot] = true;
+        dip_image_destroy(iv);
+    }
+    int rc2 = dip_sync(ctx);
+    return rc != DIP_OK ? rc : rc2;
+}
+
+}  // extern "C"

@@ -220,7 +220,18 @@ class Context:
         outs = (C.c_void_p * len(ops))(*[o.ctypes.data for o in host_out])
         check(lib().dip_run_ops_host(self._h, a.ctypes.data, w, hgt, c, n, arr, len(ops), outs, chunk_frames), self._h)
 
+    def pipeline(self, width: int, height: int, channels: int, chunk_frames: int, ops) -> "Pipeline":
+        return Pipeline(self, width, height, channels, chunk_frames, ops)
+
     # -- timing ---------------------------------------------------------------------------------
+    def mark(self, slot: int):
+        check(lib().dip_mark(self._h, slot), self._h)
+
+    def elapsed(self, slot_a: int, slot_b: int) -> float:
+        ms = C.c_float()
+        check(lib().dip_elapsed(self._h, slot_a, slot_b, C.byref(ms)), self._h)
+        return float(ms.value)
+
     def timer_start(self):
         check(lib().dip_timer_start(self._h), self._h)
 
@@ -246,6 +257,28 @@ class Context:
         arr = np.frombuffer(buf, dtype=dtype).reshape(shape)
         _PINNED[arr.ctypes.data] = p.value
         return arr
+
+
+class Pipeline:
+    """Persistent upload -> ops -> download pipeline over host rings (dip_pipeline_*)."""
+
+    def __init__(self, ctx: Context, width: int, height: int, channels: int, chunk_frames: int, ops):
+        self.ctx = ctx
+        self._ops = (capi.Op * len(ops))(*ops)
+        self.n_ops = len(ops)
+        self.chunk = chunk_frames
+        self._h = C.c_void_p()
+        check(lib().dip_pipeline_create(ctx._h, width, height, channels, chunk_frames, self._ops, len(ops), C.byref(self._h)), ctx._h)
+
+    def run(self, host_in: np.ndarray, frames: int, host_out: list[np.ndarray]):
+        """host_in: (in_ring, H, W, C); host_out[i]: (out_ring, H, W, C); rings are multiples of chunk."""
+        outs = (C.c_void_p * self.n_ops)(*[o.ctypes.data for o in host_out])
+        check(lib().dip_pipeline_run(self._h, host_in.ctypes.data, host_in.shape[0], frames, outs, host_out[0].shape[0]), self.ctx._h)
+
+    def close(self):
+        if self._h:
+            lib().dip_pipeline_destroy(self._h)
+            self._h = C.c_void_p(None)
 
 
 _PINNED: dict[int, int] = {}

@@ -202,10 +202,25 @@ DIP_API int dip_run_ops_host(dip_ctx* ctx, const uint8_t* host_in, int width, in
                              int channels, int frames, const dip_op* ops, int n_ops,
                              uint8_t* const* host_out, int chunk_frames);
 
+/* The same pipeline with its device buffers and events kept across calls, and the host side
+ * addressed as rings (a streaming source and sink): frame f is read from
+ * host_in[f % in_ring_frames] and op i's result is written to host_out[i][f % out_ring_frames].
+ * Both ring sizes must be multiples of chunk_frames.  Returns after the last download. */
+typedef struct dip_pipeline dip_pipeline;
+DIP_API int dip_pipeline_create(dip_ctx* ctx, int width, int height, int channels, int chunk_frames,
+                                const dip_op* ops, int n_ops, dip_pipeline** pipe);
+DIP_API int dip_pipeline_run(dip_pipeline* pipe, const uint8_t* host_in, int in_ring_frames, int frames,
+                             uint8_t* const* host_out, int out_ring_frames);
+DIP_API int dip_pipeline_destroy(dip_pipeline* pipe);
+
 /* ---- device-side timing on the ctx's compute stream (measure_time opencv:26-38,
  *      sycl:25-39 use a host clock; these are CUDA events) --------------------------- */
 DIP_API int dip_timer_start(dip_ctx* ctx);
 DIP_API int dip_timer_stop(dip_ctx* ctx, float* elapsed_ms); /* synchronises */
+/* lap markers: dip_mark records CUDA event `slot` on the compute stream (slots grow on demand);
+ * dip_elapsed waits for slot_b and returns the device time between two recorded slots */
+DIP_API int dip_mark(dip_ctx* ctx, int slot);
+DIP_API int dip_elapsed(dip_ctx* ctx, int slot_a, int slot_b, float* elapsed_ms);
 /* number of kernels this ctx has launched since dip_init (bench.py's gpu_launches) */
 DIP_API int dip_launch_count(const dip_ctx* ctx, uint64_t* launches);
 /* write `bytes` of scratch device memory to evict L2 between timed iterations */
