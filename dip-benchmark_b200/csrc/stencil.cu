@@ -18,8 +18,9 @@
 //    walks down its rows keeping the vertical window in registers.  Bytes are unpacked once
 //    per row into packed u16x2 lanes (even / odd bytes); a tap at +-C bytes is a compile-time
 //    selection of neighbouring packed words (at most one PRMT funnel).  Minima use the
-//    VIMNMX3.U16x2 instruction, Gaussian weights are integers evaluated with packed IMADs, and
-//    rounding reproduces OpenCV exactly: round-half-even of the exact sum for filter2D
+//    VIMNMX3.U16x2 instruction, Gaussian weights are integers evaluated with packed IMADs (the
+//    FMA pipe; the integer ALU pipe issues at half rate on sm_100, so PRMT/LOP3/LEA are the
+//    expensive instructions here), and rounding reproduces OpenCV exactly: round-half-even of the exact sum for filter2D
 //    (a fused separable pass rounds its u8 intermediate just as the reference's `aux` image
 //    is rounded), round-half-up for GaussianBlur.
 //  * Outputs leave as 16-byte coalesced stores; nothing but the source tile and the result
@@ -40,8 +41,6 @@ constexpr int kTileBytes = 512;                       // interior bytes per tile
 constexpr int kHalo = 16;                             // halo bytes either side
 constexpr int kRowBytes = kTileBytes + 2 * kHalo;     // 544 bytes per shared-memory row
 constexpr int kBoxWords = kRowBytes / 4;
-constexpr int kWarps = 4;
-constexpr int kThreads = kWarps * 32;
 
 enum StencilOp {
     kErodeSq3 = 0,    // 3x3 all-ones min (also the fused 1x3+3x1)
@@ -138,23 +137,23 @@ struct Acc8 {
     uint32_t v[8];
 };
 
-// horizontal [1 2 1] (sum <= 1020 per lane)
-template <int C>
+// horizontal [1 2 1] (sum <= 1020 per lane) plus a per-lane rounding bias folded into the first add
+template <int C, uint32_t BIAS>
 __device__ __forceinline__ void hsum3(const Row8& r, Acc8& h) {
 #define DIP_H3(j)                                                                                     \
-    h.v[2 * j] = pair_at<4 * j - C>(r) + pair_at<4 * j + C>(r) + 2u * r.e[2 + j];                     \
-    h.v[2 * j + 1] = pair_at<4 * j + 1 - C>(r) + pair_at<4 * j + 1 + C>(r) + 2u * r.o[2 + j];
+    h.v[2 * j] = (pair_at<4 * j - C>(r) + pair_at<4 * j + C>(r) + BIAS) + 2u * r.e[2 + j];            \
+    h.v[2 * j + 1] = (pair_at<4 * j + 1 - C>(r) + pair_at<4 * j + 1 + C>(r) + BIAS) + 2u * r.o[2 + j];
     DIP_H3(0) DIP_H3(1) DIP_H3(2) DIP_H3(3)
 #undef DIP_H3
 }
 
-// horizontal [1 4 6 4 1] (sum <= 4080 per lane)
-template <int C>
+// horizontal [1 4 6 4 1] (sum <= 4080 per lane) plus a per-lane rounding bias folded into the first add
+template <int C, uint32_t BIAS>
 __device__ __forceinline__ void hsum5(const Row8& r, Acc8& h) {
 #define DIP_H5(j)                                                                                     \
-    h.v[2 * j] = (pair_at<4 * j - 2 * C>(r) + pair_at<4 * j + 2 * C>(r)) +                            \
+    h.v[2 * j] = (pair_at<4 * j - 2 * C>(r) + pair_at<4 * j + 2 * C>(r) + BIAS) +                     \
                  4u * (pair_at<4 * j - C>(r) + pair_at<4 * j + C>(r)) + 6u * r.e[2 + j];              \
-    h.v[2 * j + 1] = (pair_at<4 * j + 1 - 2 * C>(r) + pair_at<4 * j + 1 + 2 * C>(r)) +                \
+    h.v[2 * j + 1] = (pair_at<4 * j + 1 - 2 * C>(r) + pair_at<4 * j + 1 + 2 * C>(r) + BIAS) +         \
                      4u * (pair_at<4 * j + 1 - C>(r) + pair_at<4 * j + 1 + C>(r)) + 6u * r.o[2 + j];
     DIP_H5(0) DIP_H5(1) DIP_H5(2) DIP_H5(3)
 #undef DIP_H5
@@ -171,8 +170,14 @@ __device__ __forceinline__ void hmnmx3(const Row8& r, Acc8& h) {
 
 // Lanes hold X = value * 256 (plus nothing); returns the lanes whose HIGH byte is
 // round-half-even(X / 256).  X + 0x7F must already be folded in by the caller.
+template <int VAR>
 __device__ __forceinline__ uint32_t rne_finish(uint32_t x_plus_7f) {
-    return x_plus_7f + ((x_plus_7f >> 8) & 0x00010001u);
+    if constexpr (VAR & 1) {
+        // bit 8 of each lane moved to bit 0 by the high half of a 32x32 multiply: one LOP3 + one IMAD.HI
+        return __umulhi(x_plus_7f & 0x01000100u, 1u << 24) + x_plus_7f;
+    } else {
+        return x_plus_7f + ((x_plus_7f >> 8) & 0x00010001u);
+    }
 }
 // results in the high byte of each lane -> 4 output bytes
 __device__ __forceinline__ uint32_t pack_hi(uint32_t ev, uint32_t od) { return __byte_perm(ev, od, 0x7351); }
@@ -181,12 +186,15 @@ __device__ __forceinline__ uint32_t pack_lo(uint32_t ev, uint32_t od) { return _
 
 // Round a packed horizontal sum to u8 exactly like the reference's intermediate image and
 // keep it scaled by 2^S in the lane (T = t << S), so the vertical pass needs no re-shift.
-template <int S>
-__device__ __forceinline__ uint32_t round_keep_scaled(uint32_t sum) {
-    constexpr uint32_t half_m1 = ((1u << (S - 1)) - 1u) * 0x00010001u;
+// `r` = sum + (2^(S-1) - 1) per lane (the bias is folded into the horizontal sum by the caller).
+template <int S, int VAR>
+__device__ __forceinline__ uint32_t round_keep_scaled(uint32_t r) {
     constexpr uint32_t keep = ~(((1u << S) - 1u) * 0x00010001u);
-    const uint32_t r = sum + half_m1;
-    return (r + ((r >> S) & 0x00010001u)) & keep;
+    if constexpr (VAR & 1) {
+        return (__umulhi(r & (0x00010001u << S), 1u << (32 - S)) + r) & keep;
+    } else {
+        return (r + ((r >> S) & 0x00010001u)) & keep;
+    }
 }
 
 __device__ __forceinline__ void load_row(const uint8_t* rowp, Row8& r) {
@@ -210,7 +218,7 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 
 // Rewrites the halo bytes/rows of the tile that lie outside the image.  `tile` row t holds
 // source row (ytop + t); byte l of a row holds source byte (bx0 - kHalo + l).
-template <int OP, int C, int ROWS>
+template <int OP, int C, int ROWS, int kThreads>
 __device__ void patch_borders(uint8_t* tile, const StencilParams& p, int bx0, int ytop) {
     constexpr int r = op_radius(OP);
     constexpr bool morph = op_is_morph(OP);
@@ -272,9 +280,10 @@ __device__ void patch_borders(uint8_t* tile, const StencilParams& p, int bx0, in
 }
 
 // ---- the tiled kernel -------------------------------------------------------------------------
-template <int OP, int C, int R>
-__global__ void __launch_bounds__(kThreads) stencil_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
+template <int OP, int C, int R, int kWarps, int VAR>
+__global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
     constexpr int r = op_radius(OP);
+    constexpr int kThreads = kWarps * 32;
     constexpr int TH = kWarps * R;
     constexpr int ROWS = TH + 2 * r;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -302,7 +311,7 @@ __global__ void __launch_bounds__(kThreads) stencil_kernel(const __grid_constant
     const bool border = bx0 == 0 || bx0 + kTileBytes + r * C > p.rowbytes || ytop < p.valid_y0 || ytop + ROWS > p.valid_y1;
     if (border) {
         __syncthreads();
-        patch_borders<OP, C, ROWS>(tile, p, bx0, ytop);
+        patch_borders<OP, C, ROWS, kThreads>(tile, p, bx0, ytop);
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -362,10 +371,10 @@ __global__ void __launch_bounds__(kThreads) stencil_kernel(const __grid_constant
         Row8 row;
         auto hpass = [&](const uint8_t* rp, Acc8& h) {
             load_row(rp, row);
-            hsum3<C>(row, h);
+            hsum3<C, OP == kConv3Sep ? 0x00010001u : 0u>(row, h);
             if constexpr (OP == kConv3Sep) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) h.v[k] = round_keep_scaled<2>(h.v[k]);  // 4 * RNE(sum / 4)
+                for (int k = 0; k < 8; ++k) h.v[k] = round_keep_scaled<2, VAR>(h.v[k]);  // 4 * RNE(sum / 4)
             }
         };
         hpass(colp, h0);
@@ -381,7 +390,7 @@ __global__ void __launch_bounds__(kThreads) stencil_kernel(const __grid_constant
                 if constexpr (OP == kGauss3) {
                     res[k] = u * 16u + h1.v[k] * 32u + 0x00800080u;          // (S + 8) >> 4
                 } else {
-                    res[k] = rne_finish(u * 16u + h1.v[k] * 32u + 0x007F007Fu);
+                    res[k] = rne_finish<VAR>(u * 16u + h1.v[k] * 32u + 0x007F007Fu);
                 }
             }
             __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch),
@@ -394,10 +403,10 @@ __global__ void __launch_bounds__(kThreads) stencil_kernel(const __grid_constant
         Row8 row;
         auto hpass = [&](const uint8_t* rp, Acc8& h) {
             load_row(rp, row);
-            hsum5<C>(row, h);
+            hsum5<C, OP == kConv5Sep ? 0x00070007u : 0u>(row, h);
             if constexpr (OP == kConv5Sep) {
 #pragma unroll
-                for (int k = 0; k < 8; ++k) h.v[k] = round_keep_scaled<4>(h.v[k]);  // 16 * RNE(sum / 16)
+                for (int k = 0; k < 8; ++k) h.v[k] = round_keep_scaled<4, VAR>(h.v[k]);  // 16 * RNE(sum / 16)
             }
         };
         hpass(colp, h0);
@@ -412,7 +421,7 @@ __global__ void __launch_bounds__(kThreads) stencil_kernel(const __grid_constant
             for (int k = 0; k < 8; ++k) {
                 // X = sum of [1 4 6 4 1] x h <= 65280: result in the high byte after RNE
                 const uint32_t x = (h0.v[k] + h4.v[k] + 0x007F007Fu) + 4u * (h1.v[k] + h3.v[k]) + 6u * h2.v[k];
-                res[k] = rne_finish(x);
+                res[k] = rne_finish<VAR>(x);
             }
             __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch),
                    make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7])));
@@ -421,9 +430,10 @@ __global__ void __launch_bounds__(kThreads) stencil_kernel(const __grid_constant
     }
 }
 
-template <int OP, int C, int R>
+template <int OP, int C, int R, int kWarps, int VAR>
 int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
     constexpr int r = op_radius(OP);
+    constexpr int kThreads = kWarps * 32;
     constexpr int TH = kWarps * R;
     constexpr int ROWS = TH + 2 * r;
     constexpr int smem_bytes = ROWS * kRowBytes + 16;
@@ -444,21 +454,38 @@ int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGe
     static std::atomic<uint64_t> attr_set{0};  // per instantiation, one bit per device
     const uint64_t dev_bit = 1ull << (ctx->device & 63);
     if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
-        DIP_CUDA(ctx, cudaFuncSetAttribute(stencil_kernel<OP, C, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        DIP_CUDA(ctx, cudaFuncSetAttribute(stencil_kernel<OP, C, R, kWarps, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
-    stencil_kernel<OP, C, R><<<(unsigned)blocks, kThreads, smem_bytes, ctx->compute>>>(*map, p);
+    stencil_kernel<OP, C, R, kWarps, VAR><<<(unsigned)blocks, kThreads, smem_bytes, ctx->compute>>>(*map, p);
     DIP_CHECK_LAUNCH(ctx, "stencil_kernel");
     return DIP_OK;
 }
 
+// Tuning hook (development only): DIP_TUNE="R,WARPS,VAR" selects another instantiation for
+// 3-channel images; unset, every op uses its tuned default.
+struct Tune { int R, warps, var; };
+Tune tune_override() {
+    static Tune t = [] {
+        Tune v{0, 0, 0};
+        if (const char* e = getenv("DIP_TUNE")) sscanf(e, "%d,%d,%d", &v.R, &v.warps, &v.var);
+        return v;
+    }();
+    return t;
+}
+
 template <int OP>
 int launch_tiled_c(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
-    constexpr int R = 16;
     switch (src->v.channels) {
-        case 1: return launch_tiled<OP, 1, R>(ctx, src, dst, g);
-        case 3: return launch_tiled<OP, 3, R>(ctx, src, dst, g);
-        case 4: return launch_tiled<OP, 4, R>(ctx, src, dst, g);
+        case 1: return launch_tiled<OP, 1, 16, 4, 1>(ctx, src, dst, g);
+        case 4: return launch_tiled<OP, 4, 16, 4, 1>(ctx, src, dst, g);
+        case 3: {
+            const Tune t = tune_override();
+#define DIP_TRY(RR, WW, VV) if (t.R == RR && t.warps == WW && t.var == VV) return launch_tiled<OP, 3, RR, WW, VV>(ctx, src, dst, g);
+            DIP_TRY(16, 4, 0) DIP_TRY(32, 2, 1) DIP_TRY(8, 4, 1) DIP_TRY(8, 8, 1)
+#undef DIP_TRY
+            return launch_tiled<OP, 3, 16, 4, 1>(ctx, src, dst, g);
+        }
     }
     return fail(ctx, DIP_ERR_ARG, "bad channel count");
 }
