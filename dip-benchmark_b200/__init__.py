@@ -14,6 +14,7 @@ The directory is named ``dip-benchmark_b200`` (not an identifier); load it with
 from .capi import DipError, lib, lib_path, build_library, declared_symbols  # noqa: F401
 from .ops import Context, Image, REFERENCE_OPS  # noqa: F401
 from . import shard  # noqa: F401
+from . import mosaic  # noqa: F401
 
 __all__ = ["Context", "Image", "DipError", "REFERENCE_OPS", "lib", "lib_path", "build_library",
-           "declared_symbols", "shard"]
+           "declared_symbols", "shard", "mosaic"]

@@ -122,6 +122,8 @@ def lib() -> C.CDLL:
         "dip_flush_l2": ([vp], i),
         "dip_synth_fill": ([vp, vp, C.c_uint32, C.c_uint64], i),
         "dip_checksum": ([vp, vp, P(C.c_uint64)], i),
+        "dip_checksum_rows": ([vp, vp, C.c_uint64, P(C.c_uint64)], i),
+        "dip_synth_fill_rows": ([vp, vp, C.c_uint32, C.c_uint64], i),
         "dip_image_ipc_export": ([vp, vp, P(IpcHandle)], i),
         "dip_image_ipc_import": ([vp, P(IpcHandle), i, i, i, i, sz, sz, P(vp)], i),
         "dip_copy_rows": ([vp, vp, i, vp, i, i], i),

@@ -575,7 +575,7 @@ int dip_flush_l2(dip_ctx* ctx) {
     return launch_fill(ctx, ctx->flush_buf, ctx->flush_bytes, 0);
 }
 
-int dip_checksum(dip_ctx* ctx, const dip_image* img, uint64_t* per_frame) {
+int dip_checksum_rows(dip_ctx* ctx, const dip_image* img, uint64_t first_row, uint64_t* per_frame) {
     if (!ctx || !img || !per_frame) return fail(ctx, DIP_ERR_ARG, "null argument");
     int rc = begin_op(ctx, img, nullptr);
     if (rc != DIP_OK) return rc;
@@ -587,18 +587,25 @@ int dip_checksum(dip_ctx* ctx, const dip_image* img, uint64_t* per_frame) {
         ctx->d_checksums_cap = n;
     }
     DIP_CUDA(ctx, cudaMemsetAsync(ctx->d_checksums, 0, sizeof(uint64_t) * (size_t)n, ctx->compute));
-    rc = launch_checksum(ctx, img->v, ctx->d_checksums);
+    rc = launch_checksum(ctx, img->v, first_row, ctx->d_checksums);
     if (rc != DIP_OK) return rc;
     DIP_CUDA(ctx, cudaMemcpyAsync(per_frame, ctx->d_checksums, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->compute));
     DIP_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     return DIP_OK;
 }
 
-int dip_synth_fill(dip_ctx* ctx, dip_image* img, uint32_t seed, uint64_t first_frame) {
+int dip_checksum(dip_ctx* ctx, const dip_image* img, uint64_t* per_frame) { return dip_checksum_rows(ctx, img, 0, per_frame); }
+
+int dip_synth_fill_rows(dip_ctx* ctx, dip_image* img, uint32_t seed, uint64_t first_row) {
     if (!ctx || !img) return fail(ctx, DIP_ERR_ARG, "null argument");
     int rc = begin_op(ctx, nullptr, img);
     if (rc != DIP_OK) return rc;
-    return launch_synth(ctx, img->v, seed, first_frame);
+    return launch_synth(ctx, img->v, seed, first_row);
+}
+
+int dip_synth_fill(dip_ctx* ctx, dip_image* img, uint32_t seed, uint64_t first_frame) {
+    if (!img) return fail(ctx, DIP_ERR_ARG, "null argument");
+    return dip_synth_fill_rows(ctx, img, seed, first_frame * (uint64_t)img->v.height);
 }
 
 // ---- IPC + row copies for mosaic bands ---------------------------------------------------

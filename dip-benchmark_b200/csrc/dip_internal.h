@@ -107,8 +107,8 @@ enum PointOp { kCopy = 0, kInvert = 1, kThreshold = 2 };
 int launch_point(dip_ctx* ctx, PointOp op, const ImgView& src, const ImgView& dst, uint8_t thresh,
                  uint8_t maxval);
 int launch_grayscale(dip_ctx* ctx, const ImgView& src, const ImgView& dst);
-int launch_synth(dip_ctx* ctx, const ImgView& dst, uint32_t seed, uint64_t first_frame);
-int launch_checksum(dip_ctx* ctx, const ImgView& src, uint64_t* d_out);
+int launch_synth(dip_ctx* ctx, const ImgView& dst, uint32_t seed, uint64_t first_row);
+int launch_checksum(dip_ctx* ctx, const ImgView& src, uint64_t first_row, uint64_t* d_out);
 int launch_fill(dip_ctx* ctx, uint8_t* p, size_t bytes, uint32_t value);
 
 // ---- stencils (stencil.cu) ------------------------------------------------------------

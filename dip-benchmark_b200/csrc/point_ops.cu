@@ -141,7 +141,7 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint64_t idx, uint32_t seed) 
     return x;
 }
 
-__global__ void __launch_bounds__(kThreads) synth_kernel(ImgView dst, uint32_t seed, uint64_t first_frame, int vec_per_row,
+__global__ void __launch_bounds__(kThreads) synth_kernel(ImgView dst, uint32_t seed, uint64_t first_row, int vec_per_row,
                                                          size_t total) {
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= total) return;
@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kThreads) synth_kernel(ImgView dst, uint32_t s
     const int vx = (int)(i - row * (size_t)vec_per_row);
     const size_t f = row / (size_t)dst.height;
     const size_t y = row - f * (size_t)dst.height;
-    const uint64_t rowbase = ((first_frame + f) * (uint64_t)dst.height + y) * (uint64_t)dst.rowbytes;
+    const uint64_t rowbase = (first_row + f * (uint64_t)dst.height + y) * (uint64_t)dst.rowbytes;
     uint32_t w[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(kThreads) synth_kernel(ImgView dst, uint32_t s
     *(reinterpret_cast<uint4*>(dst.base + f * dst.frame_stride + y * dst.pitch) + vx) = make_uint4(w[0], w[1], w[2], w[3]);
 }
 
-__global__ void __launch_bounds__(kThreads) checksum_kernel(ImgView src, int vec_per_row, size_t vec_per_frame,
+__global__ void __launch_bounds__(kThreads) checksum_kernel(ImgView src, int vec_per_row, size_t vec_per_frame, uint64_t first_row,
                                                             unsigned long long* __restrict__ out) {
     // grid.y = frame; grid-stride over the frame's vectors
     const size_t f = blockIdx.y;
@@ -181,7 +181,7 @@ __global__ void __launch_bounds__(kThreads) checksum_kernel(ImgView src, int vec
             for (int b = 0; b < 4; ++b) {
                 const int x = vx * 16 + k * 4 + b;
                 if (x < src.rowbytes) {
-                    const uint64_t pos = (uint64_t)y * (uint64_t)src.rowbytes + (uint64_t)x;
+                    const uint64_t pos = (first_row + (uint64_t)y) * (uint64_t)src.rowbytes + (uint64_t)x;
                     acc += (unsigned long long)(((w[k] >> (8 * b)) & 0xFFu) + 1u) * (unsigned long long)mix32(pos, 0x1234567u);
                 }
             }
@@ -243,23 +243,23 @@ int launch_grayscale(dip_ctx* ctx, const ImgView& src, const ImgView& dst) {
     return DIP_OK;
 }
 
-int launch_synth(dip_ctx* ctx, const ImgView& dst, uint32_t seed, uint64_t first_frame) {
+int launch_synth(dip_ctx* ctx, const ImgView& dst, uint32_t seed, uint64_t first_row) {
     const int vpr = (dst.rowbytes + 15) / 16;
     const size_t total = (size_t)vpr * (size_t)dst.height * (size_t)dst.frames;
     const size_t blocks = (total + kThreads - 1) / kThreads;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-    synth_kernel<<<(unsigned)blocks, kThreads, 0, ctx->compute>>>(dst, seed, first_frame, vpr, total);
+    synth_kernel<<<(unsigned)blocks, kThreads, 0, ctx->compute>>>(dst, seed, first_row, vpr, total);
     DIP_CHECK_LAUNCH(ctx, "synth_kernel");
     return DIP_OK;
 }
 
-int launch_checksum(dip_ctx* ctx, const ImgView& src, uint64_t* d_out) {
+int launch_checksum(dip_ctx* ctx, const ImgView& src, uint64_t first_row, uint64_t* d_out) {
     const int vpr = (src.rowbytes + 15) / 16;
     const size_t vpf = (size_t)vpr * (size_t)src.height;
     if (src.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "more than 65535 frames");
     const unsigned bx = (unsigned)std::min<size_t>((vpf + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
     dim3 grid(bx ? bx : 1, (unsigned)src.frames);
-    checksum_kernel<<<grid, kThreads, 0, ctx->compute>>>(src, vpr, vpf, reinterpret_cast<unsigned long long*>(d_out));
+    checksum_kernel<<<grid, kThreads, 0, ctx->compute>>>(src, vpr, vpf, first_row, reinterpret_cast<unsigned long long*>(d_out));
     DIP_CHECK_LAUNCH(ctx, "checksum_kernel");
     return DIP_OK;
 }

@@ -89,10 +89,23 @@ class Image:
         check(lib().dip_image_rows(self.ctx._h, self._h, row0, rows, C.byref(h)), self.ctx._h)
         return Image(self.ctx, h.value, parent=self)
 
-    def checksum(self) -> list[int]:
+    def checksum(self, first_row: int = 0) -> list[int]:
         out = (C.c_uint64 * self.frames)()
-        check(lib().dip_checksum(self.ctx._h, self._h, out), self.ctx._h)
+        check(lib().dip_checksum_rows(self.ctx._h, self._h, first_row, out), self.ctx._h)
         return [int(v) for v in out]
+
+    def synth_fill_rows(self, seed: int, first_row: int) -> "Image":
+        check(lib().dip_synth_fill_rows(self.ctx._h, self._h, seed & 0xFFFFFFFF, first_row), self.ctx._h)
+        return self
+
+    def ipc_export(self) -> bytes:
+        h = capi.IpcHandle()
+        check(lib().dip_image_ipc_export(self.ctx._h, self._h, C.byref(h)), self.ctx._h)
+        return bytes(h.bytes)
+
+    def copy_rows_from(self, src: "Image", src_row: int, dst_row: int, rows: int):
+        """Stream-ordered (halo stream) copy of rows from `src` (possibly on a peer GPU) into this image."""
+        check(lib().dip_copy_rows(self.ctx._h, src._h, src_row, self._h, dst_row, rows), self.ctx._h)
 
     def synth_fill(self, seed: int = 0, first_frame: int = 0) -> "Image":
         check(lib().dip_synth_fill(self.ctx._h, self._h, seed & 0xFFFFFFFF, first_frame), self.ctx._h)
@@ -136,6 +149,16 @@ class Context:
         h = C.c_void_p()
         check(lib().dip_image_create_batch(self._h, width, height, channels, frames, C.byref(h)), self._h)
         return Image(self, h.value)
+
+    def ipc_import(self, handle: bytes, width: int, height: int, channels: int = 1, frames: int = 1) -> Image:
+        h = capi.IpcHandle()
+        C.memmove(h.bytes, handle, 64)
+        out = C.c_void_p()
+        check(lib().dip_image_ipc_import(self._h, C.byref(h), width, height, channels, frames, 0, 0, C.byref(out)), self._h)
+        return Image(self, out.value)
+
+    def halo_fence(self):
+        check(lib().dip_halo_fence(self._h), self._h)
 
     def image_like(self, other: Image) -> Image:
         return self.image(other.width, other.height, other.channels, other.frames)

@@ -230,8 +230,14 @@ DIP_API int dip_flush_l2(dip_ctx* ctx);
 /* byte i of frame f := hash32(global byte index, seed) >> 24; frame numbering starts at
  * first_frame so that shards of one batch are generated independently per GPU */
 DIP_API int dip_synth_fill(dip_ctx* ctx, dip_image* img, uint32_t seed, uint64_t first_frame);
+/* the same generator addressed by global row: byte x of row y of frame f := hash32(((first_row +
+ * f*height + y) * row_bytes + x), seed) >> 24 -- a row band of a tall mosaic fills only its own rows */
+DIP_API int dip_synth_fill_rows(dip_ctx* ctx, dip_image* img, uint32_t seed, uint64_t first_row);
 /* position-weighted 64-bit checksum of every frame's valid bytes -> host array [frames] */
 DIP_API int dip_checksum(dip_ctx* ctx, const dip_image* img, uint64_t* per_frame);
+/* as dip_checksum with row y weighted as global row first_row + y: the checksums of the row bands
+ * of a mosaic add up (mod 2^64) to the checksum of the whole mosaic */
+DIP_API int dip_checksum_rows(dip_ctx* ctx, const dip_image* img, uint64_t first_row, uint64_t* per_frame);
 
 /* ---- multi-GPU mosaic row bands (BASELINE.json config 5) ---------------------------
  * A band holds rows [row0, row0+rows) of a tall single-frame mosaic plus `halo` rows

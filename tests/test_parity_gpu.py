@@ -247,3 +247,26 @@ def test_error_behaviour(ctx, dip):
         ctx.erode(a, ctx.image(32, 16, 3), np.zeros((3, 3), np.uint8))  # empty mask
     ctx.invert(a, a)                              # in-place point op is allowed
     ctx.sync()
+
+
+def test_mosaic_bands_with_halo_exchange_single_gpu(ctx, dip, orc):
+    """BASELINE.json config 5 at reduced size: bands + pulled halos (dip_copy_rows) == whole-image oracle,
+    and the band checksums add up to the checksum of the whole result."""
+    width, rows = 2100, 777
+    whole = orc.synth(width, rows, 1, seed=4, frame=0)
+    want = orc.erode(orc.filter2d(whole, orc.BLUR_5X5), orc.SQUARE_MASK)
+    want_cs = orc.checksum(want)
+    for world in (1, 2, 3, 5):
+        bands = [dip.mosaic.MosaicBand(ctx, width, rows, world, r) for r in range(world)]
+        for b in bands:
+            b.fill_synthetic(seed=4)
+        for b in bands:
+            b.connect_local(bands)
+        for overlap in (True, False):
+            for b in bands:
+                b.step(overlap=overlap)
+            out = np.concatenate([b.result().download() for b in bands], axis=0)
+            assert np.array_equal(out, want), (world, overlap)
+        assert sum(b.checksum() for b in bands) & 0xFFFFFFFFFFFFFFFF == want_cs, world
+        for b in bands:
+            b.close()
