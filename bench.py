@@ -397,13 +397,36 @@ def run_per_op(args) -> None:
     for r in rows:
         r["single_frac"] = r["single_gbs"] / peak
         r["batch_frac"] = r["batch_gbs"] / peak
+    # Upload / Download (opencv:92-93): PCIe-bound; pinned = one async copy, pageable = staged slices
+    import numpy as np
+    xfer = []
+    nb = 8
+    pin = ctx.pinned_empty((nb, H, W, C)); pin[...] = 7
+    page = np.full((nb, H, W, C), 9, np.uint8)
+    stack = ctx.image(W, H, C, frames=nb)
+    for name, buf in (("pinned", pin), ("pageable", page)):
+        for direction in ("upload", "download"):
+            fn = (lambda: stack.upload(buf)) if direction == "upload" else (lambda: stack.download(buf, sync=False))
+            fn(); ctx.sync()
+            t0 = time.perf_counter()
+            for _ in range(3):
+                fn()
+            ctx.sync()
+            dt = (time.perf_counter() - t0) / 3
+            xfer.append({"op": f"{direction} ({name} host memory, {nb} frames per call)", "ms_per_frame": dt / nb * 1e3,
+                         "gbs": nb * FRAME_BYTES / dt / 1e9})
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "per_op.json"), "w") as f:
-        json.dump({"peak_gbs": peak, "peak_source": peak_src, "rows": rows, "batch": args.batch}, f, indent=1)
+        json.dump({"peak_gbs": peak, "peak_source": peak_src, "rows": rows, "batch": args.batch, "transfers": xfer}, f, indent=1)
     print(f"| op | single us | GB/s | frac | batch us/frame | GB/s | frac | Mpx/s |")
     print("|---|---|---|---|---|---|---|---|")
     for r in rows:
         print(f"| {r['op']} | {r['single_us']:.2f} | {r['single_gbs']:.0f} | {r['single_frac']:.2f} | {r['batch_us_per_frame']:.2f} | {r['batch_gbs']:.0f} | {r['batch_frac']:.2f} | {r['batch_mpix_s']:.0f} |")
+    print()
+    print("| transfer | ms per 3504x2336 RGB frame | GB/s |")
+    print("|---|---|---|")
+    for x in xfer:
+        print(f"| {x['op']} | {x['ms_per_frame']:.3f} | {x['gbs']:.1f} |")
     ctx.close()
 
 

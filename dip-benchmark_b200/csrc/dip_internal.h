@@ -6,6 +6,8 @@
 #include <cuda_runtime.h>
 
 #include <cstdarg>
+#include <cstdlib>
+#include <utility>
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
@@ -92,6 +94,36 @@ int fail_cuda(const dip_ctx* ctx, cudaError_t e, const char* what, const char* f
         if (_e != cudaSuccess) return dip::fail_cuda((ctx), _e, name, __FILE__, __LINE__); \
         (ctx)->launches++;                                                        \
     } while (0)
+
+// Programmatic dependent launch: every kernel of the library is launched with the
+// programmatic-stream-serialization attribute, signals `launch_dependents` at its start and
+// executes `griddepcontrol.wait` before its first global-memory access, so the CTA launch and
+// prologue of operation i+1 overlap the tail of operation i (the reference's loops issue
+// thousands of ~10 us kernels back to back).  DIP_NO_PDL=1 disables the attribute.
+inline bool pdl_enabled() {
+    static const bool on = [] { const char* e = getenv("DIP_NO_PDL"); return !(e && e[0] == '1'); }();
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
 
 // Make the compute stream wait for outstanding copies on the operands, and set the device.
 int begin_op(dip_ctx* ctx, const dip_image* src, dip_image* dst);

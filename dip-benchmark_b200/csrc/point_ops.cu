@@ -6,7 +6,7 @@
 // cv.bitwise_not / cvtColor / threshold (/root/reference/benchmarks/opencv/benchmark.py:95-97).
 //
 // Design: the image stack is a dense byte stream (pitch = rowbytes rounded to 16), so the
-// byte-wise ops run over it as 16-byte vectors: every thread has UNROLL independent
+// byte-wise ops run over it as 16-byte vectors: every thread has two independent
 // 128-bit loads in flight before its first store, streaming (evict-first) cache policy on
 // both sides because every byte is touched exactly once.  Grayscale works on 48-byte groups
 // (16 BGR pixels = 3 vectors) with OpenCV's 15-bit BT.601 weights evaluated by two dp4a per
@@ -20,7 +20,6 @@ namespace dip {
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kUnroll = 4;
 
 __device__ __forceinline__ uint4 ld_stream(const uint4* p) { return __ldcs(p); }
 __device__ __forceinline__ void st_stream(uint4* p, const uint4& v) { __stcs(p, v); }
@@ -58,21 +57,25 @@ __device__ __forceinline__ uint4 point_vec(uint4 v, uint32_t t4, uint32_t m4) {
     return v;
 }
 
-// Dense stream: one CTA per chunk of kThreads*kUnroll vectors.
-template <int OP>
+// Dense stream: one CTA per chunk of kThreads*UNROLL consecutive vectors.  Concurrently running
+// CTAs touch neighbouring chunks, which keeps DRAM pages open; a machine-sized persistent grid
+// with one long span per CTA measured 12 % slower on B200 (1184 scattered streams).
+template <int OP, int UNROLL>
 __global__ void __launch_bounds__(kThreads) point_flat_kernel(const uint4* __restrict__ src,
                                                               uint4* __restrict__ dst, size_t nvec,
                                                               uint32_t t4, uint32_t m4) {
-    const size_t base = (size_t)blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
-    uint4 v[kUnroll];
-    if (base + (size_t)(kUnroll - 1) * kThreads < nvec) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t base = (size_t)blockIdx.x * (kThreads * UNROLL) + threadIdx.x;
+    uint4 v[UNROLL];
+    if (base + (size_t)(UNROLL - 1) * kThreads < nvec) {
 #pragma unroll
-        for (int j = 0; j < kUnroll; ++j) v[j] = ld_stream(src + base + (size_t)j * kThreads);
+        for (int j = 0; j < UNROLL; ++j) v[j] = ld_stream(src + base + (size_t)j * kThreads);
 #pragma unroll
-        for (int j = 0; j < kUnroll; ++j) st_stream(dst + base + (size_t)j * kThreads, point_vec<OP>(v[j], t4, m4));
+        for (int j = 0; j < UNROLL; ++j) st_stream(dst + base + (size_t)j * kThreads, point_vec<OP>(v[j], t4, m4));
     } else {
 #pragma unroll
-        for (int j = 0; j < kUnroll; ++j) {
+        for (int j = 0; j < UNROLL; ++j) {
             const size_t i = base + (size_t)j * kThreads;
             if (i < nvec) st_stream(dst + i, point_vec<OP>(ld_stream(src + i), t4, m4));
         }
@@ -83,6 +86,8 @@ __global__ void __launch_bounds__(kThreads) point_flat_kernel(const uint4* __res
 template <int OP>
 __global__ void __launch_bounds__(kThreads) point_rows_kernel(ImgView src, ImgView dst, int vec_per_row,
                                                               size_t total, uint32_t t4, uint32_t m4) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= total) return;
     const size_t row = i / (size_t)vec_per_row;
@@ -96,6 +101,8 @@ __global__ void __launch_bounds__(kThreads) point_rows_kernel(ImgView src, ImgVi
 
 // BGR grayscale: a thread converts one 48-byte group = 16 pixels = 3 vectors.
 __global__ void __launch_bounds__(kThreads) gray3_kernel(ImgView src, ImgView dst, int groups_per_row, size_t total) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= total) return;
     const size_t row = i / (size_t)groups_per_row;
@@ -143,6 +150,8 @@ __host__ __device__ __forceinline__ uint32_t mix32(uint64_t idx, uint32_t seed) 
 
 __global__ void __launch_bounds__(kThreads) synth_kernel(ImgView dst, uint32_t seed, uint64_t first_row, int vec_per_row,
                                                          size_t total) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
     if (i >= total) return;
     const size_t row = i / (size_t)vec_per_row;
@@ -167,6 +176,8 @@ __global__ void __launch_bounds__(kThreads) synth_kernel(ImgView dst, uint32_t s
 
 __global__ void __launch_bounds__(kThreads) checksum_kernel(ImgView src, int vec_per_row, size_t vec_per_frame, uint64_t first_row,
                                                             unsigned long long* __restrict__ out) {
+    pdl_launch_dependents();
+    pdl_wait();
     // grid.y = frame; grid-stride over the frame's vectors
     const size_t f = blockIdx.y;
     unsigned long long acc = 0;
@@ -203,17 +214,25 @@ template <int OP>
 int launch_point_t(dip_ctx* ctx, const ImgView& src, const ImgView& dst, uint32_t t4, uint32_t m4) {
     if (dense_pair(src, dst)) {
         const size_t nvec = src.pitch * (size_t)src.height * (size_t)src.frames / 16;
-        const size_t chunk = (size_t)kThreads * kUnroll;
+        // 2 x 16 B per thread measured best on B200 for one image (8.8 us) and for stacks (6.98 TB/s);
+        // DIP_PT_UNROLL=1|4|8 selects the other instantiations (development only).
+        static const int tune_unroll = [] { const char* e = getenv("DIP_PT_UNROLL"); return e ? atoi(e) : 0; }();
+        const int unroll = tune_unroll ? tune_unroll : 2;
+        const size_t chunk = (size_t)kThreads * unroll;
         const size_t blocks = (nvec + chunk - 1) / chunk;
         if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-        point_flat_kernel<OP><<<(unsigned)blocks, kThreads, 0, ctx->compute>>>(
-            reinterpret_cast<const uint4*>(src.base), reinterpret_cast<uint4*>(dst.base), nvec, t4, m4);
+        const uint4* sp = reinterpret_cast<const uint4*>(src.base);
+        uint4* dp = reinterpret_cast<uint4*>(dst.base);
+        if (unroll == 2) DIP_CUDA(ctx, launch_kernel(point_flat_kernel<OP, 2>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, sp, dp, nvec, t4, m4));
+        else if (unroll == 8) DIP_CUDA(ctx, launch_kernel(point_flat_kernel<OP, 8>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, sp, dp, nvec, t4, m4));
+        else if (unroll == 1) DIP_CUDA(ctx, launch_kernel(point_flat_kernel<OP, 1>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, sp, dp, nvec, t4, m4));
+        else DIP_CUDA(ctx, launch_kernel(point_flat_kernel<OP, 4>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, sp, dp, nvec, t4, m4));
     } else {
         const int vpr = (src.rowbytes + 15) / 16;
         const size_t total = (size_t)vpr * (size_t)src.height * (size_t)src.frames;
         const size_t blocks = (total + kThreads - 1) / kThreads;
         if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-        point_rows_kernel<OP><<<(unsigned)blocks, kThreads, 0, ctx->compute>>>(src, dst, vpr, total, t4, m4);
+        DIP_CUDA(ctx, launch_kernel(point_rows_kernel<OP>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, vpr, total, t4, m4));
     }
     DIP_CHECK_LAUNCH(ctx, "point kernel");
     return DIP_OK;
@@ -238,7 +257,7 @@ int launch_grayscale(dip_ctx* ctx, const ImgView& src, const ImgView& dst) {
     const size_t total = (size_t)groups * (size_t)src.height * (size_t)src.frames;
     const size_t blocks = (total + kThreads - 1) / kThreads;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-    gray3_kernel<<<(unsigned)blocks, kThreads, 0, ctx->compute>>>(src, dst, groups, total);
+    DIP_CUDA(ctx, launch_kernel(gray3_kernel, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total));
     DIP_CHECK_LAUNCH(ctx, "gray3_kernel");
     return DIP_OK;
 }
@@ -248,7 +267,7 @@ int launch_synth(dip_ctx* ctx, const ImgView& dst, uint32_t seed, uint64_t first
     const size_t total = (size_t)vpr * (size_t)dst.height * (size_t)dst.frames;
     const size_t blocks = (total + kThreads - 1) / kThreads;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-    synth_kernel<<<(unsigned)blocks, kThreads, 0, ctx->compute>>>(dst, seed, first_row, vpr, total);
+    DIP_CUDA(ctx, launch_kernel(synth_kernel, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, dst, seed, first_row, vpr, total));
     DIP_CHECK_LAUNCH(ctx, "synth_kernel");
     return DIP_OK;
 }
@@ -259,7 +278,8 @@ int launch_checksum(dip_ctx* ctx, const ImgView& src, uint64_t first_row, uint64
     if (src.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "more than 65535 frames");
     const unsigned bx = (unsigned)std::min<size_t>((vpf + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
     dim3 grid(bx ? bx : 1, (unsigned)src.frames);
-    checksum_kernel<<<grid, kThreads, 0, ctx->compute>>>(src, vpr, vpf, first_row, reinterpret_cast<unsigned long long*>(d_out));
+    DIP_CUDA(ctx, launch_kernel(checksum_kernel, grid, dim3(kThreads), 0, ctx->compute, src, vpr, vpf, first_row,
+                                reinterpret_cast<unsigned long long*>(d_out)));
     DIP_CHECK_LAUNCH(ctx, "checksum_kernel");
     return DIP_OK;
 }

@@ -299,12 +299,14 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
     const int y0 = p.out_y0 + ty * TH;  // first output row of the tile
     const int ytop = y0 - r;            // source row held by tile row 0
 
+    pdl_launch_dependents();
     if (threadIdx.x == 0) {
         mbar_init(bar, 1);
         fence_barrier_init();
         mbar_expect_tx(bar, ROWS * kRowBytes);
-        tma_load_3d(tile, &tmap, bar, (bx0 - kHalo) / 4, ytop, f);
     }
+    pdl_wait();  // the previous kernel's writes are visible from here on
+    if (threadIdx.x == 0) tma_load_3d(tile, &tmap, bar, (bx0 - kHalo) / 4, ytop, f);
     __syncthreads();  // barrier init visible to the waiters
     mbar_wait(bar, 0);
 
@@ -457,7 +459,7 @@ int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGe
         DIP_CUDA(ctx, cudaFuncSetAttribute(stencil_kernel<OP, C, R, kWarps, VAR>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
-    stencil_kernel<OP, C, R, kWarps, VAR><<<(unsigned)blocks, kThreads, smem_bytes, ctx->compute>>>(*map, p);
+    DIP_CUDA(ctx, launch_kernel(stencil_kernel<OP, C, R, kWarps, VAR>, dim3((unsigned)blocks), dim3(kThreads), smem_bytes, ctx->compute, *map, p));
     DIP_CHECK_LAUNCH(ctx, "stencil_kernel");
     return DIP_OK;
 }
@@ -481,8 +483,14 @@ int launch_tiled_c(dip_ctx* ctx, const dip_image* src, dip_image* dst, const Row
         case 4: return launch_tiled<OP, 4, 16, 4, 1>(ctx, src, dst, g);
         case 3: {
             const Tune t = tune_override();
+            if (t.R == 0) {
+                // Few tiles (a single image): halve the tile height so the launch is about two waves and
+                // late CTAs' loads overlap early CTAs' arithmetic; stacks keep the 64-row tile.
+                const long long tiles64 = (long long)((src->v.rowbytes + kTileBytes - 1) / kTileBytes) * ((g.out_y1 - g.out_y0 + 63) / 64) * src->v.frames;
+                if (tiles64 < 2ll * 6 * ctx->sm_count) return launch_tiled<OP, 3, 8, 4, 1>(ctx, src, dst, g);
+            }
 #define DIP_TRY(RR, WW, VV) if (t.R == RR && t.warps == WW && t.var == VV) return launch_tiled<OP, 3, RR, WW, VV>(ctx, src, dst, g);
-            DIP_TRY(16, 4, 0) DIP_TRY(32, 2, 1) DIP_TRY(8, 4, 1) DIP_TRY(8, 8, 1)
+            DIP_TRY(16, 4, 0) DIP_TRY(16, 4, 1) DIP_TRY(32, 2, 1) DIP_TRY(8, 4, 1) DIP_TRY(4, 4, 1) DIP_TRY(8, 2, 1)
 #undef DIP_TRY
             return launch_tiled<OP, 3, 16, 4, 1>(ctx, src, dst, g);
         }
@@ -505,6 +513,8 @@ template <int MODE>  // 0 erode, 1 dilate, 2 fp32 correlation
 __global__ void __launch_bounds__(256) generic_kernel(const __grid_constant__ GenericParams p) {
     const size_t total = (size_t)p.src.rowbytes * (size_t)(p.out_y1 - p.out_y0) * (size_t)p.src.frames;
     const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (i >= total) return;
     const int C = p.src.channels;
     const int xb = (int)(i % (size_t)p.src.rowbytes);
@@ -545,7 +555,7 @@ int launch_generic(dip_ctx* ctx, const GenericParams& p) {
     if (total == 0) return DIP_OK;
     const size_t blocks = (total + 255) / 256;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-    generic_kernel<MODE><<<(unsigned)blocks, 256, 0, ctx->compute>>>(p);
+    DIP_CUDA(ctx, launch_kernel(generic_kernel<MODE>, dim3((unsigned)blocks), dim3(256), 0, ctx->compute, p));
     DIP_CHECK_LAUNCH(ctx, "generic_kernel");
     return DIP_OK;
 }
