@@ -11,6 +11,7 @@
 // outstanding copy with an event, so kernels wait only when they touch such an image.
 #include <algorithm>
 #include <mutex>
+#include <thread>
 
 #include "dip_internal.h"
 
@@ -390,6 +391,29 @@ int dip_host_unregister(void* p) {
     return DIP_OK;
 }
 
+// Host-side staging copy (pageable <-> pinned) split over a few threads: one core's memcpy
+// (~12 GB/s) would otherwise cap pageable transfers far below the PCIe rate.
+static void host_copy_rows(uint8_t* dst, size_t dpitch, const uint8_t* src, size_t spitch, size_t rowbytes, int rows) {
+    static const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t total = rowbytes * (size_t)rows;
+    const unsigned nthreads = (unsigned)std::min<size_t>(std::min(8u, std::max(1u, hw / 2)), std::max<size_t>(1, total >> 20));
+    auto work = [=](unsigned t) {
+        if (dpitch == rowbytes && spitch == rowbytes) {
+            const size_t a = (total * t / nthreads) & ~(size_t)63, b = t + 1 == nthreads ? total : (total * (t + 1) / nthreads) & ~(size_t)63;
+            memcpy(dst + a, src + a, b - a);
+        } else {
+            const int r0 = (int)((size_t)rows * t / nthreads), r1 = (int)((size_t)rows * (t + 1) / nthreads);
+            for (int r = r0; r < r1; ++r) memcpy(dst + dpitch * r, src + spitch * r, rowbytes);
+        }
+    };
+    if (nthreads <= 1) { work(0); return; }
+    std::vector<std::thread> pool;
+    pool.reserve(nthreads - 1);
+    for (unsigned t = 1; t < nthreads; ++t) pool.emplace_back(work, t);
+    work(0);
+    for (auto& th : pool) th.join();
+}
+
 static bool is_pinned(const void* p) {
     cudaPointerAttributes a{};
     if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
@@ -430,8 +454,7 @@ int enqueue_upload(dip_ctx* ctx, const ImgView& v, const uint8_t* host, size_t h
             DIP_CUDA(ctx, cudaEventSynchronize(ctx->stage_up_free[slot]));
             uint8_t* st = ctx->stage_up[slot];
             const uint8_t* hsrc = host + host_pitch * ((size_t)f * v.height + y);
-            if (host_pitch == rowb) memcpy(st, hsrc, rowb * rows);
-            else for (int r = 0; r < rows; ++r) memcpy(st + rowb * r, hsrc + host_pitch * r, rowb);
+            host_copy_rows(st, rowb, hsrc, host_pitch, rowb, rows);
             DIP_CUDA(ctx, cudaMemcpy2DAsync(v.base + v.frame_stride * (size_t)f + v.pitch * (size_t)y, v.pitch, st, rowb, rowb,
                                             rows, cudaMemcpyHostToDevice, ctx->upload));
             DIP_CUDA(ctx, cudaEventRecord(ctx->stage_up_free[slot], ctx->upload));
@@ -457,8 +480,7 @@ int enqueue_download(dip_ctx* ctx, const ImgView& v, uint8_t* host, size_t host_
     auto drain = [&](int s) -> int {
         if (!pend[s].live) return DIP_OK;
         DIP_CUDA(ctx, cudaEventSynchronize(ctx->stage_dn_done[s]));
-        if (host_pitch == rowb) memcpy(pend[s].hdst, ctx->stage_dn[s], rowb * pend[s].rows);
-        else for (int r = 0; r < pend[s].rows; ++r) memcpy(pend[s].hdst + host_pitch * r, ctx->stage_dn[s] + rowb * r, rowb);
+        host_copy_rows(pend[s].hdst, host_pitch, ctx->stage_dn[s], rowb, rowb, pend[s].rows);
         pend[s].live = false;
         return DIP_OK;
     };

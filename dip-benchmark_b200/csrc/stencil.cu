@@ -52,11 +52,25 @@ enum StencilOp {
     kGauss3 = 6,      // [1 2 1]x[1 2 1]/16, round half up
     kConv5 = 7,       // [1 4 6 4 1]x[1 4 6 4 1]/256, single RNE
     kConv5Sep = 8,    // RNE(/16) rows -> u8 -> RNE(/16) columns
+    // one-dimensional passes (the reference's native harness runs the separable ops as two calls
+    // through an aux image, sycl/benchmark.cpp:341-356)
+    kErodeRow3 = 9,   // 1x3 all-ones min
+    kErodeCol3 = 10,  // 3x1
+    kDilateRow3 = 11,
+    kDilateCol3 = 12,
+    kConvRow3 = 13,   // RNE([1 2 1]/4) along x
+    kConvCol3 = 14,   // along y
+    kConvRow5 = 15,   // RNE([1 4 6 4 1]/16) along x
+    kConvCol5 = 16,   // along y
 };
 
-__host__ __device__ constexpr int op_radius(int op) { return op >= kConv5 ? 2 : 1; }
-__host__ __device__ constexpr bool op_is_morph(int op) { return op <= kDilateCross3; }
-__host__ __device__ constexpr bool op_is_dilate(int op) { return op == kDilateSq3 || op == kDilateCross3; }
+__host__ __device__ constexpr bool op_is_row_only(int op) { return op == kErodeRow3 || op == kDilateRow3 || op == kConvRow3 || op == kConvRow5; }
+__host__ __device__ constexpr bool op_is_col_only(int op) { return op == kErodeCol3 || op == kDilateCol3 || op == kConvCol3 || op == kConvCol5; }
+__host__ __device__ constexpr int op_taps(int op) { return (op == kConv5 || op == kConv5Sep || op == kConvRow5 || op == kConvCol5) ? 2 : 1; }
+__host__ __device__ constexpr int op_radius_x(int op) { return op_is_col_only(op) ? 0 : op_taps(op); }
+__host__ __device__ constexpr int op_radius_y(int op) { return op_is_row_only(op) ? 0 : op_taps(op); }
+__host__ __device__ constexpr bool op_is_dilate(int op) { return op == kDilateSq3 || op == kDilateCross3 || op == kDilateRow3 || op == kDilateCol3; }
+__host__ __device__ constexpr bool op_is_morph(int op) { return op <= kDilateCross3 || (op >= kErodeRow3 && op <= kDilateCol3); }
 
 struct StencilParams {
     ImgView dst;
@@ -220,14 +234,15 @@ __device__ __forceinline__ int reflect101(int p, int len) {
 // source row (ytop + t); byte l of a row holds source byte (bx0 - kHalo + l).
 template <int OP, int C, int ROWS, int kThreads>
 __device__ void patch_borders(uint8_t* tile, const StencilParams& p, int bx0, int ytop) {
-    constexpr int r = op_radius(OP);
+    constexpr int rx = op_radius_x(OP), ry = op_radius_y(OP);
     constexpr bool morph = op_is_morph(OP);
     constexpr uint8_t fill = op_is_dilate(OP) ? 0 : 255;
     const int tid = threadIdx.x;
-    const bool left = bx0 == 0;
-    const bool right = bx0 + kTileBytes + r * C > p.rowbytes;
+    const bool left = rx > 0 && bx0 == 0;
+    const bool right = rx > 0 && bx0 + kTileBytes + rx * C > p.rowbytes;
     if (left || right) {
         // columns: (row, side, d, ch)
+        constexpr int r = rx > 0 ? rx : 1;
         const int per_row = 2 * r * C;
         for (int i = tid; i < ROWS * per_row; i += kThreads) {
             const int t = i / per_row;
@@ -256,9 +271,10 @@ __device__ void patch_borders(uint8_t* tile, const StencilParams& p, int bx0, in
         }
         __syncthreads();
     }
-    const bool top = ytop < p.valid_y0;
-    const bool bottom = ytop + ROWS > p.valid_y1;
+    const bool top = ry > 0 && ytop < p.valid_y0;
+    const bool bottom = ry > 0 && ytop + ROWS > p.valid_y1;
     if (top || bottom) {
+        constexpr int r = ry;
         constexpr int vec_per_row = kRowBytes / 16;
         for (int i = tid; i < ROWS * vec_per_row; i += kThreads) {
             const int t = i / vec_per_row;
@@ -282,7 +298,8 @@ __device__ void patch_borders(uint8_t* tile, const StencilParams& p, int bx0, in
 // ---- the tiled kernel -------------------------------------------------------------------------
 template <int OP, int C, int R, int kWarps, int VAR>
 __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
-    constexpr int r = op_radius(OP);
+    constexpr int r = op_radius_y(OP);   // halo rows
+    constexpr int rx = op_radius_x(OP);  // halo pixels
     constexpr int kThreads = kWarps * 32;
     constexpr int TH = kWarps * R;
     constexpr int ROWS = TH + 2 * r;
@@ -310,7 +327,8 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
     __syncthreads();  // barrier init visible to the waiters
     mbar_wait(bar, 0);
 
-    const bool border = bx0 == 0 || bx0 + kTileBytes + r * C > p.rowbytes || ytop < p.valid_y0 || ytop + ROWS > p.valid_y1;
+    const bool border = (rx > 0 && (bx0 == 0 || bx0 + kTileBytes + rx * C > p.rowbytes)) ||
+                        (r > 0 && (ytop < p.valid_y0 || ytop + ROWS > p.valid_y1));
     if (border) {
         __syncthreads();
         patch_borders<OP, C, ROWS, kThreads>(tile, p, bx0, ytop);
@@ -325,7 +343,65 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
     const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // tile row of source row yw - r
     uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
 
-    if constexpr (op_is_morph(OP)) {
+    if constexpr (op_is_row_only(OP)) {
+        // one-dimensional pass along x: no vertical window
+        Row8 row;
+        Acc8 h;
+#pragma unroll 2
+        for (int i = 0; i < nrows; ++i) {
+            load_row(colp + i * kRowBytes, row);
+            uint32_t out[4];
+            if constexpr (op_is_morph(OP)) {
+                hmnmx3<C, op_is_dilate(OP)>(row, h);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) out[j] = pack_lo(h.v[2 * j], h.v[2 * j + 1]);
+            } else {
+                constexpr uint32_t scale = OP == kConvRow3 ? 64u : 16u;  // sum * scale has the result in the high byte
+                if constexpr (OP == kConvRow3) hsum3<C, 0u>(row, h);
+                else hsum5<C, 0u>(row, h);
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    out[j] = pack_hi(rne_finish<VAR>(h.v[2 * j] * scale + 0x007F007Fu), rne_finish<VAR>(h.v[2 * j + 1] * scale + 0x007F007Fu));
+            }
+            __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch), make_uint4(out[0], out[1], out[2], out[3]));
+        }
+    } else if constexpr (op_is_col_only(OP)) {
+        // one-dimensional pass along y: only the thread's own 4 words, vertical window of raw rows
+        constexpr int taps = op_taps(OP);
+        Acc8 w0, w1, w2, w3, w4;
+        auto load_own = [&](const uint8_t* rp, Acc8& a) {
+            const uint4 b = *reinterpret_cast<const uint4*>(rp);
+            const uint32_t w[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a.v[2 * j] = even_bytes(w[j]); a.v[2 * j + 1] = odd_bytes(w[j]); }
+        };
+        load_own(colp, w0);
+        load_own(colp + kRowBytes, w1);
+        if constexpr (taps == 2) { load_own(colp + 2 * kRowBytes, w2); load_own(colp + 3 * kRowBytes, w3); }
+#pragma unroll 2
+        for (int i = 0; i < nrows; ++i) {
+            uint32_t res[8];
+            if constexpr (taps == 1) {
+                load_own(colp + (i + 2) * kRowBytes, w2);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if constexpr (op_is_morph(OP)) res[k] = mnmx3<op_is_dilate(OP)>(w0.v[k], w1.v[k], w2.v[k]);
+                    else res[k] = rne_finish<VAR>((w0.v[k] + w2.v[k]) * 64u + w1.v[k] * 128u + 0x007F007Fu);
+                }
+                w0 = w1; w1 = w2;
+            } else {
+                load_own(colp + (i + 4) * kRowBytes, w4);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    res[k] = rne_finish<VAR>((w0.v[k] + w4.v[k]) * 16u + (w1.v[k] + w3.v[k]) * 64u + w2.v[k] * 96u + 0x007F007Fu);
+                w0 = w1; w1 = w2; w2 = w3; w3 = w4;
+            }
+            uint4 o;
+            if constexpr (op_is_morph(OP)) o = make_uint4(pack_lo(res[0], res[1]), pack_lo(res[2], res[3]), pack_lo(res[4], res[5]), pack_lo(res[6], res[7]));
+            else o = make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7]));
+            __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch), o);
+        }
+    } else if constexpr (op_is_morph(OP)) {
         constexpr bool MAX = op_is_dilate(OP);
         constexpr bool cross = OP == kErodeCross3 || OP == kDilateCross3;
         Acc8 h0, h1, h2;   // square: horizontal extrema of rows i-1, i, i+1
@@ -367,7 +443,7 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
             h1 = h2;
             __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch), make_uint4(out[0], out[1], out[2], out[3]));
         }
-    } else if constexpr (r == 1) {
+    } else if constexpr (op_taps(OP) == 1) {
         // 3-tap Gaussians.  h* hold the horizontal pass of rows i-1, i, i+1.
         Acc8 h0, h1, h2;
         Row8 row;
@@ -434,7 +510,7 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
 
 template <int OP, int C, int R, int kWarps, int VAR>
 int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
-    constexpr int r = op_radius(OP);
+    constexpr int r = op_radius_y(OP);
     constexpr int kThreads = kWarps * 32;
     constexpr int TH = kWarps * R;
     constexpr int ROWS = TH + 2 * r;
@@ -603,6 +679,8 @@ int stencil_morph(dip_ctx* ctx, Morph m, const dip_image* src, dip_image* dst, c
     for (int i = 0; i < mw * mh; ++i) nz += mask[i] != 0;
     if (nz == 0) return fail(ctx, DIP_ERR_ARG, "mask has no non-zero tap");
     const bool dil = m == Morph::Dilate;
+    if (mw == 3 && mh == 1 && nz == 3) return dil ? launch_tiled_c<kDilateRow3>(ctx, src, dst, g) : launch_tiled_c<kErodeRow3>(ctx, src, dst, g);
+    if (mw == 1 && mh == 3 && nz == 3) return dil ? launch_tiled_c<kDilateCol3>(ctx, src, dst, g) : launch_tiled_c<kErodeCol3>(ctx, src, dst, g);
     if (mw == 3 && mh == 3) {
         if (nz == 9) return dil ? launch_tiled_c<kDilateSq3>(ctx, src, dst, g) : launch_tiled_c<kErodeSq3>(ctx, src, dst, g);
         const bool cross = nz == 5 && mask[1] && mask[3] && mask[4] && mask[5] && mask[7];
@@ -628,6 +706,12 @@ int stencil_convolve(dip_ctx* ctx, const dip_image* src, dip_image* dst, const f
     if (rc != DIP_OK) return rc;
     static const int g3[9] = {1, 2, 1, 2, 4, 2, 1, 2, 1};
     static const int g5[25] = {1, 4, 6, 4, 1, 4, 16, 24, 16, 4, 6, 24, 36, 24, 6, 4, 16, 24, 16, 4, 1, 4, 6, 4, 1};
+    static const int b3[3] = {1, 2, 1};
+    static const int b5[5] = {1, 4, 6, 4, 1};
+    if (kw == 3 && kh == 1 && matches(k, 3, b3, 4.0f)) return launch_tiled_c<kConvRow3>(ctx, src, dst, g);
+    if (kw == 1 && kh == 3 && matches(k, 3, b3, 4.0f)) return launch_tiled_c<kConvCol3>(ctx, src, dst, g);
+    if (kw == 5 && kh == 1 && matches(k, 5, b5, 16.0f)) return launch_tiled_c<kConvRow5>(ctx, src, dst, g);
+    if (kw == 1 && kh == 5 && matches(k, 5, b5, 16.0f)) return launch_tiled_c<kConvCol5>(ctx, src, dst, g);
     if (kw == 3 && kh == 3 && matches(k, 9, g3, 16.0f)) return launch_tiled_c<kConv3>(ctx, src, dst, g);
     if (kw == 5 && kh == 5 && matches(k, 25, g5, 256.0f)) return launch_tiled_c<kConv5>(ctx, src, dst, g);
     GenericParams p;

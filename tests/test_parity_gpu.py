@@ -270,3 +270,36 @@ def test_mosaic_bands_with_halo_exchange_single_gpu(ctx, dip, orc):
         assert sum(b.checksum() for b in bands) & 0xFFFFFFFFFFFFFFFF == want_cs, world
         for b in bands:
             b.close()
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_one_dimensional_passes_two_call_form(ctx, dip, orc, c):
+    """The reference's native harness runs the separable ops as two calls through an aux image
+    (sycl/benchmark.cpp:341-356, opencv:76-90); each 1-D pass and the pair must match the oracle,
+    and the pair must equal the fused kernels."""
+    rng = np.random.default_rng(40 + c)
+    o = dip.ops
+    for (h, w) in [(1, 1), (2, 3), (5, 1), (1, 7), (33, 47), (70, 512), (131, 700)]:
+        img = rand_img(rng, h, w, c)
+        src = ctx.from_array(img)
+        aux = ctx.image_like(src)
+        dst = ctx.image_like(src)
+        for krow, kcol in ((o.BLUR_3X3_1X3, o.BLUR_3X3_3X1), (o.BLUR_5X5_1X5, o.BLUR_5X5_5X1)):
+            ctx.convolve(src, aux, krow)
+            assert np.array_equal(aux.download().reshape(img.shape), orc.filter2d(img, krow)), (h, w, "row")
+            ctx.convolve(src, dst, kcol)
+            assert np.array_equal(dst.download().reshape(img.shape), orc.filter2d(img, kcol)), (h, w, "col")
+            ctx.convolve(aux, dst, kcol)
+            two = dst.download().reshape(img.shape)
+            assert np.array_equal(two, orc.filter2d_separable(img, krow, kcol))
+            ctx.convolve_separable(src, dst, krow, kcol)
+            assert np.array_equal(dst.download().reshape(img.shape), two)
+        for fn, ofn in ((ctx.erode, orc.erode), (ctx.dilate, orc.dilate)):
+            fn(src, aux, o.SQUARE_MASK_1X3)
+            assert np.array_equal(aux.download().reshape(img.shape), ofn(img, o.SQUARE_MASK_1X3))
+            fn(src, dst, o.SQUARE_MASK_3X1)
+            assert np.array_equal(dst.download().reshape(img.shape), ofn(img, o.SQUARE_MASK_3X1))
+            fn(aux, dst, o.SQUARE_MASK_3X1)
+            assert np.array_equal(dst.download().reshape(img.shape), ofn(img, o.SQUARE_MASK))
+        for im in (src, aux, dst):
+            im.close()
