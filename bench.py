@@ -130,6 +130,11 @@ def cpu_sample(frames_total: int) -> dict:
             "sample": f"{frames_total} frames x 12 ops of the 3504x2336 RGB chain, one frame per thread over {cores} threads"}
 
 
+def workload_name(batch: int, world: int) -> str:
+    return (f"batch of {batch} synthetic 3504x2336 RGB u8 frames, full 12-op chain (copy, inversion, grayscale, threshold, "
+            f"3 erosions, 4 Gaussian convolutions, GaussianBlur), sharded over {world} GPU(s)")
+
+
 def run_reference_arm(args) -> None:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -148,8 +153,10 @@ def run_reference_arm(args) -> None:
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * total_s / len(vals), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "u8", "data": "synthetic", "impl": "reference",
-        "config": {"workload": f"full 12-op chain on 3504x2336 RGB u8 frames, OpenCV CPU path, {frames} frames per step (bounded sample of the 256-frame batch)",
-                   "frames_per_step": frames, "ops": 12},
+        "config": {"workload": workload_name(args.batch, int(os.environ.get("WORLD_SIZE", str(args.gpus)))),
+                   "frames_total": args.batch, "ops": 12,
+                   "sample": f"each step = {frames} frames of that batch through the reference's OpenCV CPU calls (opencv/benchmark.py:94-105) on all host cores",
+                   "frames_per_step": frames},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": info["cores"], "kind": info["kind"], "sample": info["sample"]},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -276,7 +283,7 @@ def run_ours(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8", "data": "synthetic",
-            "config": {"workload": f"batch of {args.batch} synthetic 3504x2336 RGB u8 frames, full 12-op chain (copy, inversion, grayscale, threshold, 3 erosions, 4 Gaussian convolutions, GaussianBlur), sharded over {world} GPU(s)",
+            "config": {"workload": workload_name(args.batch, world),
                        "frames_total": args.batch, "frames_per_gpu": count, "ops": n_ops, "launches_per_step": n_ops,
                        "l2": f"inputs larger than L2 ({count * FRAME_BYTES / 2**20:.0f} MiB in + same out per rank, streamed once per op)"},
             "clocks": clk.summary(),

@@ -259,10 +259,17 @@ static inline uint32_t orc_mix32(uint64_t idx, uint32_t seed) {
     return x;
 }
 
+ORC_API void orc_synth_fill_rows(uint8_t* dst, size_t pitch, int w, int h, int c, uint32_t seed, uint64_t first_row);
+
 ORC_API void orc_synth_fill(uint8_t* dst, size_t pitch, int w, int h, int c,
                             uint32_t seed, uint64_t frame) {
+    orc_synth_fill_rows(dst, pitch, w, h, c, seed, frame * (uint64_t)h);
+}
+
+/* rows addressed globally: a row band of a tall mosaic fills only its own rows */
+ORC_API void orc_synth_fill_rows(uint8_t* dst, size_t pitch, int w, int h, int c, uint32_t seed, uint64_t first_row) {
     const size_t rowb = (size_t)w * c;
-    const uint64_t base = frame * (uint64_t)h * rowb;
+    const uint64_t base = first_row * rowb;
 #pragma omp parallel for schedule(static)
     for (int y = 0; y < h; ++y) {
         uint8_t* d = dst + y * pitch;
@@ -273,7 +280,14 @@ ORC_API void orc_synth_fill(uint8_t* dst, size_t pitch, int w, int h, int c,
 
 /* 64-bit FNV-1a style checksum over the valid bytes of an image, used for
  * "checksum of checksums" comparisons at sizes too big to ship goldens for. */
+ORC_API uint64_t orc_checksum_rows(const uint8_t* src, size_t pitch, int w, int h, int c, uint64_t first_row);
+
 ORC_API uint64_t orc_checksum(const uint8_t* src, size_t pitch, int w, int h, int c) {
+    return orc_checksum_rows(src, pitch, w, h, c, 0);
+}
+
+/* rows weighted as global rows first_row + y: band checksums of a mosaic add up mod 2^64 */
+ORC_API uint64_t orc_checksum_rows(const uint8_t* src, size_t pitch, int w, int h, int c, uint64_t first_row) {
     const size_t rowb = (size_t)w * c;
     uint64_t total = 0;
 #pragma omp parallel for schedule(static) reduction(+ : total)
@@ -281,7 +295,7 @@ ORC_API uint64_t orc_checksum(const uint8_t* src, size_t pitch, int w, int h, in
         const uint8_t* s = src + y * pitch;
         uint64_t acc = 0;
         for (size_t i = 0; i < rowb; ++i) {
-            const uint64_t pos = (uint64_t)y * rowb + i;
+            const uint64_t pos = (first_row + (uint64_t)y) * rowb + i;
             acc += (uint64_t)(s[i] + 1u) * (uint64_t)orc_mix32(pos, 0x1234567u);
         }
         total += acc;

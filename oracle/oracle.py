@@ -59,6 +59,10 @@ def lib() -> C.CDLL:
         L.orc_synth_fill.restype = None
         L.orc_checksum.argtypes = [u8p, sz, i, i, i]
         L.orc_checksum.restype = C.c_uint64
+        L.orc_checksum_rows.argtypes = [u8p, sz, i, i, i, C.c_uint64]
+        L.orc_checksum_rows.restype = C.c_uint64
+        L.orc_synth_fill_rows.argtypes = [u8p, sz, i, i, i, C.c_uint32, C.c_uint64]
+        L.orc_synth_fill_rows.restype = None
         L.orc_max_threads.restype = i
         L.orc_set_threads.argtypes = [i]
         _lib = L
@@ -141,10 +145,16 @@ def synth(w: int, h: int, c: int, seed: int = 0, frame: int = 0) -> np.ndarray:
     return out
 
 
-def checksum(img) -> int:
+def synth_rows(w: int, rows: int, c: int, seed: int, first_row: int) -> np.ndarray:
+    out = np.empty((rows, w, c), dtype=np.uint8)
+    lib().orc_synth_fill_rows(out.ctypes.data, w * c, w, rows, c, seed & 0xFFFFFFFF, first_row)
+    return out
+
+
+def checksum(img, first_row: int = 0) -> int:
     a = _as3(img)
     h, w, c = a.shape
-    return int(lib().orc_checksum(a.ctypes.data, w * c, w, h, c))
+    return int(lib().orc_checksum_rows(a.ctypes.data, w * c, w, h, c, first_row))
 
 
 # The reference's operation list, opencv:94-105, as (prefix, function) in its order.

@@ -107,3 +107,14 @@ def test_numpy_restatement_of_packed_rounding():
         got = (R + ((R >> s) & 1)) >> s
         want = np.rint(S / float(1 << s)).astype(np.int64)  # numpy rint is round-half-even
         assert np.array_equal(got, want), s
+
+
+def test_row_addressed_synth_and_checksum_compose(orc):
+    """Bands of a mosaic: synth_rows stitches to the whole, band checksums add up to the whole's."""
+    whole = orc.synth(64, 50, 1, seed=3, frame=0)
+    parts = [orc.synth_rows(64, 20, 1, 3, 0), orc.synth_rows(64, 30, 1, 3, 20)]
+    assert np.array_equal(np.concatenate(parts, axis=0), whole)
+    total = (orc.checksum(parts[0], first_row=0) + orc.checksum(parts[1], first_row=20)) & 0xFFFFFFFFFFFFFFFF
+    assert total == orc.checksum(whole)
+    # frame f of a stack starts at global row f * height
+    assert np.array_equal(orc.synth(64, 50, 1, seed=3, frame=2), orc.synth_rows(64, 50, 1, 3, 100))

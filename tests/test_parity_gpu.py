@@ -303,3 +303,28 @@ def test_one_dimensional_passes_two_call_form(ctx, dip, orc, c):
             assert np.array_equal(dst.download().reshape(img.shape), ofn(img, o.SQUARE_MASK))
         for im in (src, aux, dst):
             im.close()
+
+
+def test_mosaic_known_answer_checksums(ctx, dip):
+    """BASELINE.json config 5: the oracle's checksum of the whole pipeline result (tests/golden/mosaic_kat.json,
+    computed on the CPU by make_mosaic_kat.py) against the GPU row-band driver, at 4096^2 and at the full 65536^2,
+    for 1 band and for 8 bands with pulled halos."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "mosaic_kat.json")) as f:
+        kat = json.load(f)
+    for side_s, want in sorted(kat.items(), key=lambda kv: int(kv[0])):
+        side = int(side_s)
+        for world in (1, 8):
+            if side >= 65536 and world == 8:
+                continue  # 8 x 3 band buffers of 512 MiB are fine, but one pass at full size is enough for the test budget
+            bands = [dip.mosaic.MosaicBand(ctx, side, side, world, r) for r in range(world)]
+            for b in bands:
+                b.fill_synthetic(seed=0)
+            for b in bands:
+                b.connect_local(bands)
+            for b in bands:
+                b.step()
+            got = sum(b.checksum() for b in bands) & 0xFFFFFFFFFFFFFFFF
+            for b in bands:
+                b.close()
+            assert f"{got:016x}" == want, (side, world)
