@@ -31,6 +31,9 @@ W, H, C = 3504, 2336, 3
 PIXELS = W * H
 FRAME_BYTES = PIXELS * C            # N = 24 556 032
 ALG_BYTES_PER_FRAME_OP = 2 * FRAME_BYTES  # read every input byte once + write every output byte once
+# dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per frame, from the committed
+# `ncu --set full` capture (profiles/r1_ncu_stencil_full.md: 6.287 + 6.233 GB for a 256-frame launch)
+NCU_TRAFFIC_PER_FRAME = (6.287e9 + 6.233e9) / 256
 METRIC = "mpixel_per_s_full_op_chain_3504x2336_rgb_u8_batch"
 UNIT = "Mpixel/s"
 
@@ -44,7 +47,9 @@ def measured_peak() -> tuple[float, str]:
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe).  Started before the warm-up so that
+    samples exist even when the timed region is a few milliseconds; `mark()` opens the timed window and the
+    summary uses the samples inside it (falling back to the nearest ones taken under the same load)."""
 
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -53,10 +58,12 @@ class ClockSampler:
         self.index = index
         self.rows = []
         self.proc = None
+        self.t0 = None
+        self.t1 = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -66,11 +73,19 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def mark(self):
+        if self.t0 is None:
+            self.t0 = time.time()
+        else:
+            self.t1 = time.time()
 
     def __exit__(self, *exc):
+        if self.t1 is None:
+            self.t1 = time.time()
         if self.proc:
-            time.sleep(0.15)
+            time.sleep(0.12)
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
@@ -78,17 +93,22 @@ class ClockSampler:
                 self.proc.kill()
 
     def summary(self) -> dict:
-        sm = [float(r[0]) for r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace(".", "").isdigit()]
+        rows = [(t, r) for t, r in self.rows if len(r) >= 8 and r[0].replace(".", "").isdigit()]
+        inside = [r for t, r in rows if self.t0 is not None and self.t0 <= t <= (self.t1 or t) + 0.06]
+        window = "timed region"
+        if not inside:  # timed region shorter than the sampling period: the samples taken under the warm-up load
+            inside = [r for t, r in rows if self.t0 is None or t >= self.t0 - 1.0][-6:] or [r for _, r in rows][-6:]
+            window = "nearest samples (timed region shorter than the sampling period)"
+        sm = [float(r[0]) for r in inside]
+        mx = [float(r[1]) for r in inside if r[1].replace(".", "").isdigit()]
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            if len(r) >= 8:
-                for n, v in zip(names, r[4:8]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
+        for r in inside:
+            for n, v in zip(names, r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -218,16 +238,18 @@ def run_ours(args) -> None:
             if marks_base is not None:
                 ctx.mark(marks_base + 1 + i)
 
-    for _ in range(args.warmup):
-        step()
-    barrier_sync(ctx, dist, torch)
-    launches0 = ctx.launch_count()
     stride = n_ops + 1
     with ClockSampler(local) as clk:
+        for _ in range(args.warmup):
+            step()
+        barrier_sync(ctx, dist, torch)
+        launches0 = ctx.launch_count()
+        clk.mark()
         ctx.timer_start()
         for k in range(args.steps):
             step(k * stride)
         ms_local = ctx.timer_stop()
+        clk.mark()
         barrier_sync(ctx, dist, torch)
     launches = ctx.launch_count() - launches0
     ms = max_over_ranks(ms_local, dist, torch)
@@ -270,6 +292,8 @@ def run_ours(args) -> None:
         e2e = {"value": args.batch * n_ops * PIXELS / (dt / e2e_steps) / 1e6, "unit": UNIT,
                "h2d_bytes_per_step": count * FRAME_BYTES, "d2h_bytes_per_step": count * n_ops * FRAME_BYTES,
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps, "chunk_frames": chunk,
+               "pcie_d2h_gbs_per_gpu": count * n_ops * FRAME_BYTES / (dt / e2e_steps) / 1e9,
+               "bound": "PCIe device-to-host (12 result frames leave for every frame that enters); measured pinned D2H peak on this pool is ~56-58 GB/s",
                "note": "per rank: upload each frame once, 12 ops, download all 12 results; pinned host rings; host wall clock around the C-ABI call"}
         pipe.close()
 
@@ -290,7 +314,8 @@ def run_ours(args) -> None:
             "e2e": e2e,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": ops[dom][1], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": NCU_TRAFFIC_PER_FRAME * count, "peak_source": peak_src,
+                         "traffic_source": "ncu --set full capture in profiles/ (per launch, scaled to this rank's frames)",
                          "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_ms": per_op_ms[dom]},
             "per_op": per_op,
             "cpu_baseline": cpu,
@@ -317,15 +342,17 @@ def run_mosaic(args) -> None:
         dist.all_gather_object(handles, band.export_handle())
         band.connect(handles)
     barrier_sync(ctx, dist, torch)
-    for _ in range(args.warmup):
-        band.step(overlap=not args.no_overlap)
-    barrier_sync(ctx, dist, torch)
-    launches0 = ctx.launch_count()
     with ClockSampler(local) as clk:
+        for _ in range(max(args.warmup, 20)):   # a step is < 3 ms: keep the GPU under load while clocks are sampled
+            band.step(overlap=not args.no_overlap)
+        barrier_sync(ctx, dist, torch)
+        launches0 = ctx.launch_count()
+        clk.mark()
         ctx.timer_start()
         for _ in range(args.steps):
             band.step(overlap=not args.no_overlap)
         ms_local = ctx.timer_stop()
+        clk.mark()
         barrier_sync(ctx, dist, torch)
     launches = ctx.launch_count() - launches0
     ms = max_over_ranks(ms_local, dist, torch) / args.steps

@@ -328,3 +328,43 @@ def test_mosaic_known_answer_checksums(ctx, dip):
             for b in bands:
                 b.close()
             assert f"{got:016x}" == want, (side, world)
+
+
+def test_native_cli_driver_matches_oracle(ctx, dip, orc, tmp_path):
+    """dip_bench (the reference's native harness, sycl/benchmark.cpp:389-463, on the C-ABI): exit codes, the 14 table
+    rows and the `{prefix}-{name}` outputs, checked against the oracle."""
+    import subprocess
+    exe = os.path.join(ROOT, "dip-benchmark_b200", "dip_bench")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "dip-benchmark_b200", "host"), "CXX=g++"])
+    rng = np.random.default_rng(12)
+    img = rng.integers(0, 256, (97, 211, 3), dtype=np.uint8)           # BGR as the library sees it
+    src = tmp_path / "in.ppm"
+    with open(src, "wb") as f:
+        f.write(b"P6\n211 97\n255\n" + img[:, :, ::-1].tobytes())       # PPM is RGB
+    out = tmp_path / "out"
+    assert subprocess.run([exe], capture_output=True).returncode == 1                      # usage
+    assert subprocess.run([exe, str(tmp_path / "missing.ppm"), str(out)], capture_output=True).returncode == 6
+    r = subprocess.run([exe, str(src), str(out) + "/", "3"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [l for l in r.stdout.splitlines() if l.startswith("|")]
+    assert len(rows) == 14 and "(3 times)" in rows[0] and rows[0].startswith("| Upload")
+    for prefix, ofn in orc.OPERATIONS:
+        data = open(out / f"{prefix}-in.ppm", "rb").read()
+        hdr = b"P6\n211 97\n255\n"
+        assert data.startswith(hdr)
+        got = np.frombuffer(data[len(hdr):], np.uint8).reshape(97, 211, 3)[:, :, ::-1]
+        assert np.array_equal(got, ofn(img)), prefix
+
+
+def test_python_perform_benchmark_mirror(ctx, dip, orc, tmp_path, capsys):
+    """benchmark.py = the reference's perform_benchmark (opencv:41-114) on the C-ABI."""
+    from dip_benchmark_b200 import benchmark
+    rng = np.random.default_rng(13)
+    img = rng.integers(0, 256, (64, 150, 3), dtype=np.uint8)
+    lines = []
+    outs = benchmark.perform_benchmark(img, "t.png", str(tmp_path), 2, out=lines.append)
+    assert len(lines) == 14 and lines[3].startswith("| Inversion")
+    for prefix, ofn in orc.OPERATIONS:
+        assert np.array_equal(outs[prefix], ofn(img)), prefix
+        assert os.path.exists(tmp_path / f"{prefix}-t.png")
