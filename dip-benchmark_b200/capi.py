@@ -129,6 +129,7 @@ def lib() -> C.CDLL:
         "dip_copy_rows": ([vp, vp, i, vp, i, i], i),
         "dip_halo_fence": ([vp], i),
         "dip_apply_rows": ([vp, P(Op), vp, i, i, i, i, vp, i], i),
+        "dip_debug_set": ([C.c_char_p, i], i),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)

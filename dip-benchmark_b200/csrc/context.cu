@@ -116,7 +116,7 @@ int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CU
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&key.map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, v.base, dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(ctx, DIP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %dx%d pitch %zu box %dx%d",
                     (int)r, v.width, v.height, v.pitch, box_words, box_rows);
