@@ -265,8 +265,7 @@ DIP_API int dip_apply_rows(dip_ctx* ctx, const dip_op* op, const dip_image* src,
                            int dst_row0);
 
 /* ---- development hook: kernel-selection knobs for A/B measurements inside one process.
- * keys: "stencil" (0 = automatic choice, 1 = tile kernel, 2 = strip kernel), "band" (rows per strip,
- * 0 = automatic), "stages" (ring depth of the strip kernel, 2 or 3).  Not needed by applications. */
+ * keys: "tile_rows" (stencil tile height: 0 = automatic, 64 or 32).  Not needed by applications. */
 DIP_API int dip_debug_set(const char* key, int value);
 
 #ifdef __cplusplus

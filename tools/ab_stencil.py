@@ -13,10 +13,7 @@ dst = ctx.image(3504, 2336, 3, frames=frames)
 ops = {p: op for _, p, op in ctx.reference_ops()}
 names = ["erosion-square", "gaussian-blur-3x3", "convolution-gaussian-blur-3x3", "convolution-gaussian-blur-3x3-separated",
          "convolution-gaussian-blur-5x5", "convolution-gaussian-blur-5x5-separated"]
-variants = [("tile", dict(stencil=1, band=0, stages=2))]
-for band in (16, 32, 64, 128, 256):
-    for st in (2, 3):
-        variants.append((f"strip b{band} s{st}", dict(stencil=2, band=band, stages=st)))
+variants = [("tile 64 rows", dict(tile_rows=64)), ("tile 32 rows", dict(tile_rows=32))]
 res = {(v, n): [] for v, _ in variants for n in names}
 for r in range(rounds):
     for vname, knobs in variants:
