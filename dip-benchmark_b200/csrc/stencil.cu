@@ -287,59 +287,17 @@ __device__ void patch_borders(uint8_t* tile, const StencilParams& p, int bx0, in
     }
 }
 
-// ---- the tiled kernel -------------------------------------------------------------------------
-template <int OP, int C, int R, int kWarps>
-__global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
-    constexpr int r = op_radius_y(OP);   // halo rows
-    constexpr int rx = op_radius_x(OP);  // halo pixels
-    constexpr int kThreads = kWarps * 32;
-    constexpr int TH = kWarps * R;
-    constexpr int ROWS = TH + 2 * r;
-    extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* tile = smem;
-    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + ROWS * kRowBytes);
-
-    const int b = blockIdx.x;
-    const int tx = b % p.tiles_x;
-    const int tq = b / p.tiles_x;
-    const int ty = tq % p.tiles_y;
-    const int f = tq / p.tiles_y;
-    const int bx0 = tx * kTileBytes;
-    const int y0 = p.out_y0 + ty * TH;  // first output row of the tile
-    const int ytop = y0 - r;            // source row held by tile row 0
-
-    pdl_launch_dependents();
-    if (threadIdx.x == 0) {
-        mbar_init(bar, 1);
-        fence_barrier_init();
-        mbar_expect_tx(bar, ROWS * kRowBytes);
-    }
-    pdl_wait();  // the previous kernel's writes are visible from here on
-    if (threadIdx.x == 0) tma_load_3d(tile, &tmap, bar, (bx0 - kHalo) / 4, ytop, f);
-    __syncthreads();  // barrier init visible to the waiters
-    mbar_wait(bar, 0);
-
-    const bool border = (rx > 0 && (bx0 == 0 || bx0 + kTileBytes + rx * C > p.rowbytes)) ||
-                        (r > 0 && (ytop < p.valid_y0 || ytop + ROWS > p.valid_y1));
-    if (border) {
-        __syncthreads();
-        patch_borders<OP, C, ROWS, kThreads>(tile, p, bx0, ytop);
-    }
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cx = bx0 + 16 * lane;  // first byte of this thread's column
-    if (cx >= ((p.rowbytes + 15) & ~15)) return;
-    const int yw = y0 + warp * R;    // first output row of this warp
-    if (yw >= p.out_y1) return;
-    const int nrows = min(R, p.out_y1 - yw);
-    const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // tile row of source row yw - r
-    uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
-
+// ---- the arithmetic of one warp band: the thread walks down its 16-byte column --------------------
+// FULL = the band has all R rows (compile-time trip count: the row loops unroll by the period of the
+// register window without a remainder loop); otherwise `nrows_rt` rows.
+template <int OP, int C, int R, bool FULL>
+__device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr, const StencilParams& p, int nrows_rt) {
+    const int nrows = FULL ? R : nrows_rt;
     if constexpr (op_is_row_only(OP)) {
         // one-dimensional pass along x: no vertical window
         Row8 row;
         Acc8 h;
-#pragma unroll 2
+#pragma unroll 3
         for (int i = 0; i < nrows; ++i) {
             load_row(colp + i * kRowBytes, row);
             uint32_t out[4];
@@ -370,7 +328,7 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
         load_own(colp, w0);
         load_own(colp + kRowBytes, w1);
         if constexpr (taps == 2) { load_own(colp + 2 * kRowBytes, w2); load_own(colp + 3 * kRowBytes, w3); }
-#pragma unroll 2
+#pragma unroll (op_taps(OP) == 2 ? 5 : 3)
         for (int i = 0; i < nrows; ++i) {
             uint32_t res[8];
             if constexpr (taps == 1) {
@@ -500,6 +458,54 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
     }
 }
 
+// ---- the tiled kernel -------------------------------------------------------------------------
+template <int OP, int C, int R, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
+    constexpr int r = op_radius_y(OP);   // halo rows
+    constexpr int rx = op_radius_x(OP);  // halo pixels
+    constexpr int kThreads = kWarps * 32;
+    constexpr int TH = kWarps * R;
+    constexpr int ROWS = TH + 2 * r;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* tile = smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + ROWS * kRowBytes);
+
+    const int tx = blockIdx.x, ty = blockIdx.y, f = blockIdx.z;  // x fastest: neighbouring CTAs share halos in L2
+    const int bx0 = tx * kTileBytes;
+    const int y0 = p.out_y0 + ty * TH;  // first output row of the tile
+    const int ytop = y0 - r;            // source row held by tile row 0
+
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar, ROWS * kRowBytes);
+    }
+    pdl_wait();  // the previous kernel's writes are visible from here on
+    if (threadIdx.x == 0) tma_load_3d(tile, &tmap, bar, (bx0 - kHalo) / 4, ytop, f);
+    __syncthreads();  // barrier init visible to the waiters
+    mbar_wait(bar, 0);
+
+    const bool border = (rx > 0 && (bx0 == 0 || bx0 + kTileBytes + rx * C > p.rowbytes)) ||
+                        (r > 0 && (ytop < p.valid_y0 || ytop + ROWS > p.valid_y1));
+    if (border) {
+        __syncthreads();
+        patch_borders<OP, C, ROWS, kThreads>(tile, p, bx0, ytop);
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cx = bx0 + 16 * lane;  // first byte of this thread's column
+    if (cx >= ((p.rowbytes + 15) & ~15)) return;
+    const int yw = y0 + warp * R;    // first output row of this warp
+    if (yw >= p.out_y1) return;
+    const int nrows = min(R, p.out_y1 - yw);
+    const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // tile row of source row yw - r
+    uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
+
+    if (nrows == R) compute_band<OP, C, R, true>(colp, dptr, p, R);
+    else compute_band<OP, C, R, false>(colp, dptr, p, nrows);
+}
+
 template <int OP, int C, int R, int kWarps>
 int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
     constexpr int r = op_radius_y(OP);
@@ -518,16 +524,15 @@ int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGe
     p.out_y0 = g.out_y0; p.out_y1 = g.out_y1; p.dst_y0 = g.dst_y0;
     p.tiles_x = (src->v.rowbytes + kTileBytes - 1) / kTileBytes;
     p.tiles_y = (g.out_y1 - g.out_y0 + TH - 1) / TH;
-    const long long blocks = (long long)p.tiles_x * p.tiles_y * src->v.frames;
-    if (blocks <= 0) return DIP_OK;
-    if (blocks > 0x7FFFFFFFll) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
+    if (p.tiles_x <= 0 || p.tiles_y <= 0) return DIP_OK;
+    if (p.tiles_y > 65535 || src->v.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
     static std::atomic<uint64_t> attr_set{0};  // per instantiation, one bit per device
     const uint64_t dev_bit = 1ull << (ctx->device & 63);
     if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
         DIP_CUDA(ctx, cudaFuncSetAttribute(stencil_kernel<OP, C, R, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
-    DIP_CUDA(ctx, launch_kernel(stencil_kernel<OP, C, R, kWarps>, dim3((unsigned)blocks), dim3(kThreads), smem_bytes, ctx->compute, *map, p));
+    DIP_CUDA(ctx, launch_kernel(stencil_kernel<OP, C, R, kWarps>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames), dim3(kThreads), smem_bytes, ctx->compute, *map, p));
     DIP_CHECK_LAUNCH(ctx, "stencil_kernel");
     return DIP_OK;
 }
@@ -539,14 +544,15 @@ Knobs g_knobs;
 template <int OP>
 int launch_tiled_c(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
     switch (src->v.channels) {
-        case 1: return launch_tiled<OP, 1, 16, 4>(ctx, src, dst, g);
-        case 4: return launch_tiled<OP, 4, 16, 4>(ctx, src, dst, g);
+        case 1: return launch_tiled<OP, 1, 15, 4>(ctx, src, dst, g);
+        case 4: return launch_tiled<OP, 4, 15, 4>(ctx, src, dst, g);
         case 3: {
             // Few tiles (a single image): halve the tile height so the launch is about two waves and
             // late CTAs' loads overlap early CTAs' arithmetic; stacks keep the 64-row tile.
             const long long tiles64 = (long long)((src->v.rowbytes + kTileBytes - 1) / kTileBytes) * ((g.out_y1 - g.out_y0 + 63) / 64) * src->v.frames;
-            const bool small = g_knobs.tile_rows ? g_knobs.tile_rows == 32 : tiles64 < 2ll * 6 * ctx->sm_count;
-            return small ? launch_tiled<OP, 3, 8, 4>(ctx, src, dst, g) : launch_tiled<OP, 3, 16, 4>(ctx, src, dst, g);
+            const bool small = g_knobs.tile_rows ? g_knobs.tile_rows < 60 : tiles64 < 2ll * 6 * ctx->sm_count;
+            constexpr int kSmallR = op_taps(OP) == 2 ? 10 : 9;  // multiples of the window period (5 / 3 rows)
+            return small ? launch_tiled<OP, 3, kSmallR, 4>(ctx, src, dst, g) : launch_tiled<OP, 3, 15, 4>(ctx, src, dst, g);
         }
     }
     return fail(ctx, DIP_ERR_ARG, "bad channel count");

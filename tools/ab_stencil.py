@@ -1,5 +1,5 @@
-"""Interleaved A/B timing of stencil kernel variants inside one process (same GPU, same clocks).
-usage: python tools/ab_stencil.py [frames=256] [rounds=4]"""
+"""Interleaved timing of the stencil ops inside one process (same GPU, same clocks).
+usage: python tools/ab_stencil.py [frames=256] [rounds=4] [knob=value,...;knob=value,...]"""
 import os, sys, statistics
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from _dip_pkg import load
@@ -7,13 +7,15 @@ dip = load()
 L = dip.lib()
 frames = int(sys.argv[1]) if len(sys.argv) > 1 else 256
 rounds = int(sys.argv[2]) if len(sys.argv) > 2 else 4
+variants = [("default", {})]
+if len(sys.argv) > 3:
+    variants = [(v, dict((kv.split("=")[0], int(kv.split("=")[1])) for kv in v.split(",") if kv)) for v in sys.argv[3].split(";")]
 ctx = dip.Context(0)
 src = ctx.image(3504, 2336, 3, frames=frames).synth_fill(seed=0)
 dst = ctx.image(3504, 2336, 3, frames=frames)
 ops = {p: op for _, p, op in ctx.reference_ops()}
-names = ["erosion-square", "gaussian-blur-3x3", "convolution-gaussian-blur-3x3", "convolution-gaussian-blur-3x3-separated",
-         "convolution-gaussian-blur-5x5", "convolution-gaussian-blur-5x5-separated"]
-variants = [("tile 64 rows", dict(tile_rows=64)), ("tile 32 rows", dict(tile_rows=32))]
+names = ["inversion", "grayscale", "erosion-cross", "erosion-square", "gaussian-blur-3x3", "convolution-gaussian-blur-3x3",
+         "convolution-gaussian-blur-3x3-separated", "convolution-gaussian-blur-5x5", "convolution-gaussian-blur-5x5-separated"]
 res = {(v, n): [] for v, _ in variants for n in names}
 for r in range(rounds):
     for vname, knobs in variants:
