@@ -160,6 +160,13 @@ class Context:
     def halo_fence(self):
         check(lib().dip_halo_fence(self._h), self._h)
 
+    def wrap(self, device_ptr: int, width: int, height: int, channels: int, frames: int = 1, pitch: int = 0,
+             frame_stride: int = 0, keepalive=None) -> Image:
+        """Borrow caller-owned device memory (dip_image_wrap): e.g. a region of interest of a larger image."""
+        h = C.c_void_p()
+        check(lib().dip_image_wrap(self._h, C.c_void_p(device_ptr), width, height, channels, frames, pitch, frame_stride, C.byref(h)), self._h)
+        return Image(self, h.value, parent=keepalive)
+
     def image_like(self, other: Image) -> Image:
         return self.image(other.width, other.height, other.channels, other.frames)
 

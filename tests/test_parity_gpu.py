@@ -368,3 +368,40 @@ def test_python_perform_benchmark_mirror(ctx, dip, orc, tmp_path, capsys):
     for prefix, ofn in orc.OPERATIONS:
         assert np.array_equal(outs[prefix], ofn(img)), prefix
         assert os.path.exists(tmp_path / f"{prefix}-t.png")
+
+
+def test_wrapped_regions_of_interest_with_foreign_pitch(ctx, dip, orc):
+    """dip_image_wrap on a region of interest of a larger image: pitch > row bytes, real pixels right of the
+    region (they must NOT leak into the border handling), different pitches for src and dst."""
+    rng = np.random.default_rng(21)
+    for c in (1, 3, 4):
+        big = rng.integers(0, 256, (90, 640, c), dtype=np.uint8)
+        parent = ctx.from_array(big)
+        x0 = 32 if c != 3 else 16          # x0 * c must be a multiple of 16 bytes
+        w, h, y0 = 333, 61, 7
+        roi = big[y0:y0 + h, x0:x0 + w]
+        src = ctx.wrap(parent.device_ptr + y0 * parent.pitch + x0 * c, w, h, c, pitch=parent.pitch, keepalive=parent)
+        outbig = ctx.image(700, 80, c)      # destination region inside another image with another pitch
+        dst = ctx.wrap(outbig.device_ptr + 3 * outbig.pitch + 48, w, h, c, pitch=outbig.pitch, keepalive=outbig)  # 48 bytes in
+        for (prefix, name, args), (_, ofn) in zip(dip.REFERENCE_OPS, orc.OPERATIONS):
+            getattr(ctx, name)(src, dst, *args)
+            full = outbig.download()
+            got = full.reshape(80, -1)[3:3 + h, 48:48 + w * c].reshape(h, w, c)
+            assert np.array_equal(got, ofn(roi)), f"{prefix} c={c}"
+        src.close(); dst.close(); parent.close(); outbig.close()
+
+
+def test_randomized_shapes_and_ops(ctx, dip, orc):
+    """Seeded random geometry sweep (ragged widths around the 512-byte tile and 60/36-row tile boundaries)."""
+    rng = np.random.default_rng(2026)
+    widths = [1, 2, 5, 6, 43, 85, 170, 171, 172, 341, 342, 343, 511, 512, 513, 700]
+    heights = [1, 2, 3, 4, 9, 10, 11, 35, 36, 37, 59, 60, 61, 119, 121, 150]
+    for trial in range(40):
+        w = int(rng.choice(widths)); h = int(rng.choice(heights)); c = int(rng.choice([1, 3, 4])); n = int(rng.choice([1, 1, 2, 9]))
+        stack = rng.integers(0, 256, (n, h, w, c), dtype=np.uint8)
+        k = int(rng.integers(0, len(dip.REFERENCE_OPS)))
+        prefix, name, args = dip.REFERENCE_OPS[k]
+        ofn = orc.OPERATIONS[k][1]
+        got = run_op(ctx, name, args, stack)
+        for f in range(n):
+            assert np.array_equal(got[f], ofn(stack[f])), f"trial {trial}: {prefix} {n}x{h}x{w}x{c} frame {f}"
