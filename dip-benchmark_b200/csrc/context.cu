@@ -65,6 +65,7 @@ static int new_image(dip_ctx* ctx, dip_image** out) {
     dip_image* im = new (std::nothrow) dip_image();
     if (!im) return fail(ctx, DIP_ERR_NOMEM, "out of host memory");
     im->ctx = ctx;
+    im->device = ctx ? ctx->device : -1;
     cudaError_t e = cudaEventCreateWithFlags(&im->copy_done, cudaEventDisableTiming);
     if (e != cudaSuccess) {
         delete im;
@@ -348,7 +349,7 @@ int dip_image_rows(dip_ctx* ctx, dip_image* parent, int row0, int rows, dip_imag
 
 int dip_image_destroy(dip_image* im) {
     if (!im) return DIP_OK;
-    if (im->ctx) cudaSetDevice(im->ctx->device);
+    if (im->device >= 0) cudaSetDevice(im->device);
     if (im->copy_pending) cudaEventSynchronize(im->copy_done);
     if (im->copy_done) cudaEventDestroy(im->copy_done);
     if (im->ipc_mapped && im->alloc) cudaIpcCloseMemHandle(im->alloc);
@@ -361,7 +362,7 @@ int dip_image_get_info(const dip_image* im, dip_image_info* info) {
     if (!im || !info) return fail(nullptr, DIP_ERR_ARG, "null argument");
     info->width = im->v.width; info->height = im->v.height; info->channels = im->v.channels;
     info->frames = im->v.frames; info->pitch = im->v.pitch; info->frame_stride = im->v.frame_stride;
-    info->device_ptr = im->v.base; info->device = im->ctx ? im->ctx->device : -1;
+    info->device_ptr = im->v.base; info->device = im->device;
     return DIP_OK;
 }
 

@@ -35,7 +35,8 @@ struct TmapKey {
 }  // namespace dip
 
 struct dip_image {
-    dip_ctx* ctx = nullptr;
+    dip_ctx* ctx = nullptr;      // may be gone by the time the image is destroyed: never dereferenced there
+    int device = -1;
     dip::ImgView v{};
     void* alloc = nullptr;       // cudaMalloc'ed block when owned
     bool owned = false;

@@ -3,10 +3,12 @@
 // "| desc | once | N times |" (sycl:368), same output files "{prefix}-{filename}" (sycl:374).
 //
 // The reference links OpenCV only for imread/imwrite (sycl:445,:374); OpenCV's C++ library is not
-// part of this image, so this driver reads and writes binary PNM (P5 gray / P6 RGB) itself.  P6 is
-// RGB while cv::imread gives BGR: the channels are swapped on load and store so the grayscale
-// weights meet the same colours as in the reference.  `benchmark.py` next to the library is the
-// same harness for any format cv2/PIL can decode.
+// part of this image, so this driver does its own image I/O:
+//  * .jpg / .jpeg through nvJPEG (jpeg_io.cpp): the file is decoded straight into the device image and every
+//    result is encoded from device memory and written as `{prefix}-{filename}` exactly like the reference;
+//  * binary PNM (P5 gray / P6 RGB) natively.  P6 is RGB while cv::imread gives BGR: the channels are swapped
+//    on load and store so the grayscale weights meet the same colours as in the reference.
+// `benchmark.py` next to the library is the same harness for any format cv2/PIL can decode.
 //
 // Extra flags after ROUNDS: --no-sync (enqueue-only timing like the reference's OpenCV harness),
 // --device N, --batch N (replicate the image N times and run every op on the stack).
@@ -23,6 +25,7 @@
 #include <vector>
 
 #include "dip.h"
+#include "jpeg_io.h"
 
 namespace ch = std::chrono;
 namespace fs = std::filesystem;
@@ -97,8 +100,24 @@ static bool write_pnm(const std::string& path, const uint8_t* bgr, int w, int h,
         }                                                                                        \
     } while (0)
 
+static bool has_jpeg_ext(const fs::path& p) {
+    std::string e = p.extension().string();
+    for (auto& ch_ : e) ch_ = (char)tolower(ch_);
+    return e == ".jpg" || e == ".jpeg";
+}
+
+static bool read_file(const std::string& path, std::vector<uint8_t>& out) {
+    std::ifstream in(path, std::ios::binary | std::ios::ate);
+    if (!in) return false;
+    const std::streamsize n = in.tellg();
+    in.seekg(0);
+    out.resize((size_t)n);
+    return (bool)in.read(reinterpret_cast<char*>(out.data()), n);
+}
+
+// `image.data` empty + jpeg != nullptr: the pixels are decoded from `jpeg_bytes` directly into the device image.
 static void perform_benchmark(dip_ctx* ctx, const Pnm& image, const std::string& filename, const fs::path& outdir, size_t rounds,
-                              bool sync_every_call, int batch) {
+                              bool sync_every_call, int batch, JpegIo* jpeg, const std::vector<uint8_t>& jpeg_bytes) {
     const int width = image.w, height = image.h, channels = image.c;
     const size_t frame_bytes = (size_t)width * height * channels;
     dip_image *d_input = nullptr, *d_output = nullptr;                              // sycl:260-262 (no d_aux: fused separable ops)
@@ -107,7 +126,24 @@ static void perform_benchmark(dip_ctx* ctx, const Pnm& image, const std::string&
     uint8_t *h_in = nullptr, *h_out = nullptr;                                      // pinned host buffers for the transfer path
     CHECK(dip_host_alloc(reinterpret_cast<void**>(&h_in), frame_bytes * batch));
     CHECK(dip_host_alloc(reinterpret_cast<void**>(&h_out), frame_bytes * batch));
-    for (int b = 0; b < batch; ++b) std::memcpy(h_in + frame_bytes * b, image.data.data(), frame_bytes);
+    if (jpeg) {
+        // decode on the GPU into frame 0 of the input stack, then replicate / fetch the pixels for the Upload row
+        dip_image_info info;
+        CHECK(dip_image_get_info(d_input, &info));
+        std::string err;
+        if (!jpeg_io_decode(jpeg, jpeg_bytes, info.device_ptr, info.pitch, width, height, &err)) {
+            std::fprintf(stderr, "Error: %s\n", err.c_str());
+            std::exit(6);
+        }
+        dip_image* f0 = nullptr;
+        CHECK(dip_image_view(ctx, d_input, 0, 1, &f0));
+        CHECK(dip_download(ctx, f0, h_in, 0));
+        CHECK(dip_sync(ctx));
+        dip_image_destroy(f0);
+        for (int b = 1; b < batch; ++b) std::memcpy(h_in + frame_bytes * b, h_in, frame_bytes);
+    } else {
+        for (int b = 0; b < batch; ++b) std::memcpy(h_in + frame_bytes * b, image.data.data(), frame_bytes);
+    }
     CHECK(dip_upload(ctx, d_input, h_in, 0));                                       // sycl:264
     CHECK(dip_sync(ctx));
 
@@ -130,6 +166,20 @@ static void perform_benchmark(dip_ctx* ctx, const Pnm& image, const std::string&
         auto [once, times] = measure_time(func, rounds, sync);
         std::printf("| %-*s | %10.6fs (once) | %10.6fs (%zu times) |\n", biggest, description.c_str(), once, times, rounds);
         if (prefix.empty()) continue;
+        if (jpeg) {  // encode frame 0 of the result on the GPU; only the bitstream comes back
+            dip_image_info info;
+            CHECK(dip_image_get_info(d_output, &info));
+            CHECK(dip_sync(ctx));
+            std::vector<uint8_t> bits;
+            std::string err;
+            if (!jpeg_io_encode(jpeg, info.device_ptr, info.pitch, width, height, &bits, &err)) {
+                std::fprintf(stderr, "Error: %s\n", err.c_str());
+                continue;
+            }
+            std::ofstream out((outdir / (prefix + "-" + filename)).string(), std::ios::binary);   // sycl:374
+            out.write(reinterpret_cast<const char*>(bits.data()), (std::streamsize)bits.size());
+            continue;
+        }
         CHECK(dip_download(ctx, d_output, h_out, 0));
         CHECK(dip_sync(ctx));
         const std::string stem = fs::path(filename).stem().string();
@@ -170,7 +220,7 @@ int main(int argc, char** argv) {
         }
     }
     fs::path inpath(pos[0]);
-    if (!inpath.has_filename()) { std::fprintf(stderr, "Error: [INPUT IMAGE] must be an image file (binary PGM/PPM)\n"); return 2; }  // sycl:417-421
+    if (!inpath.has_filename()) { std::fprintf(stderr, "Error: [INPUT IMAGE] must be an image file, e.g. JPG, PGM, PPM\n"); return 2; }  // sycl:417-421
     fs::path outpath(pos[1]);
 
     dip_ctx* ctx = nullptr;
@@ -184,12 +234,23 @@ int main(int argc, char** argv) {
     std::printf("Platform: CUDA sm_%d%d, %d SMs (%s)\n", info.cc_major, info.cc_minor, info.sm_count, dip_version());
 
     Pnm image;
-    if (!read_pnm(inpath.string(), image)) {                                                              // sycl:445-449
+    JpegIo* jpeg = nullptr;
+    std::vector<uint8_t> jpeg_bytes;
+    if (has_jpeg_ext(inpath)) {
+        std::string err;
+        if (!read_file(inpath.string(), jpeg_bytes) || !(jpeg = jpeg_io_create(&err)) ||
+            !jpeg_io_info(jpeg, jpeg_bytes, &image.w, &image.h, &err)) {                                  // sycl:445-449
+            std::fprintf(stderr, "Error: Failed to load image from '%s' %s\n", inpath.string().c_str(), err.c_str());
+            return 6;
+        }
+        image.c = 3;  // cv::imread delivers BGR for JPEG input
+    } else if (!read_pnm(inpath.string(), image)) {
         std::fprintf(stderr, "Error: Failed to load image from '%s'\n", inpath.string().c_str());
         return 6;
     }
     if (!fs::exists(outpath)) fs::create_directories(outpath);                                            // sycl:452-454
-    perform_benchmark(ctx, image, inpath.filename().string(), outpath, rounds, sync_every_call, batch);  // sycl:460
+    perform_benchmark(ctx, image, inpath.filename().string(), outpath, rounds, sync_every_call, batch, jpeg, jpeg_bytes);  // sycl:460
+    jpeg_io_destroy(jpeg);
     dip_shutdown(ctx);
     return 0;
 }

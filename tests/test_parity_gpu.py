@@ -405,3 +405,29 @@ def test_randomized_shapes_and_ops(ctx, dip, orc):
         got = run_op(ctx, name, args, stack)
         for f in range(n):
             assert np.array_equal(got[f], ofn(stack[f])), f"trial {trial}: {prefix} {n}x{h}x{w}x{c} frame {f}"
+
+
+def test_native_cli_driver_jpeg_through_nvjpeg(ctx, dip, orc, tmp_path):
+    """dip_bench on the reference's own input (assets/fundus.jpg = data/fundus.jpg): decoded on the GPU by nvJPEG,
+    results encoded on the GPU and written as `{prefix}-fundus.jpg` like the reference (opencv:114, sycl:374).
+    Decoder and encoder are lossy and differ from libjpeg-turbo, so the files are compared by PSNR only."""
+    import subprocess
+    cv2 = pytest.importorskip("cv2")
+    exe = os.path.join(ROOT, "dip-benchmark_b200", "dip_bench")
+    if not os.path.exists(exe):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "dip-benchmark_b200", "host"), "CXX=g++"])
+    src = os.path.join(ROOT, "data", "fundus.jpg")
+    out = tmp_path / "results"
+    r = subprocess.run([exe, src, str(out) + "/", "2"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    rows = [l for l in r.stdout.splitlines() if l.startswith("|")]
+    assert len(rows) == 14
+    img = cv2.imread(src)
+    for prefix, ofn in orc.OPERATIONS:
+        got = cv2.imread(str(out / f"{prefix}-fundus.jpg"))
+        assert got is not None and got.shape == img.shape, prefix
+        want = ofn(img).astype(np.float64)
+        mse = np.mean((got.astype(np.float64) - want) ** 2)
+        psnr = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+        # threshold output is a hard 0/255 image of a noisy channel: JPEG ringing and decoder differences flip pixels
+        assert psnr > (18.0 if prefix == "threshold" else 30.0), (prefix, psnr)
