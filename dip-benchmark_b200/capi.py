@@ -106,6 +106,7 @@ def lib() -> C.CDLL:
         "dip_convolve": ([vp, vp, vp, vp, i, i], i),
         "dip_convolve_separable": ([vp, vp, vp, vp, i, vp, i], i),
         "dip_gaussian_blur3x3": ([vp, vp, vp], i),
+        "dip_gauss5x5_erode3x3": ([vp, vp, vp], i),
         "dip_apply": ([vp, P(Op), vp, vp], i),
         "dip_reference_ops": ([P(Op), i], i),
         "dip_reference_op_prefix": ([i], C.c_char_p),

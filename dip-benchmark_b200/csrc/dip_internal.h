@@ -159,6 +159,7 @@ int stencil_convolve(dip_ctx* ctx, const dip_image* src, dip_image* dst, const f
 int stencil_convolve_sep(dip_ctx* ctx, const dip_image* src, dip_image* dst, const float* krow,
                          int kw, const float* kcol, int kh, const RowGeom& g);
 int stencil_gaussian3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g);
+int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g);
 
 // TMA descriptor of an image view seen as a (pitch/4 words, rows, frames) u32 tensor.
 int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out);

@@ -105,6 +105,7 @@ int dip_apply(dip_ctx* ctx, const dip_op* op, const dip_image* src, dip_image* d
         case DIP_OP_CONVOLVE: return dip_convolve(ctx, src, dst, op->kernel, op->kw, op->kh);
         case DIP_OP_CONVOLVE_SEPARABLE: return dip_convolve_separable(ctx, src, dst, op->kernel, op->kw, op->kernel_col, op->kh);
         case DIP_OP_GAUSSIAN_BLUR3X3: return dip_gaussian_blur3x3(ctx, src, dst);
+        case DIP_OP_GAUSS5X5_ERODE3X3: return dip_gauss5x5_erode3x3(ctx, src, dst);
     }
     return fail(ctx, DIP_ERR_ARG, "unknown operation kind %d", op->kind);
 }
@@ -144,6 +145,7 @@ extern "C" int dip_apply_rows(dip_ctx* ctx, const dip_op* op, const dip_image* s
         case DIP_OP_CONVOLVE: return stencil_convolve(ctx, src, dst, op->kernel, op->kw, op->kh, g);
         case DIP_OP_CONVOLVE_SEPARABLE: return stencil_convolve_sep(ctx, src, dst, op->kernel, op->kw, op->kernel_col, op->kh, g);
         case DIP_OP_GAUSSIAN_BLUR3X3: return stencil_gaussian3(ctx, src, dst, g);
+        case DIP_OP_GAUSS5X5_ERODE3X3: return stencil_gauss5_erode3(ctx, src, dst, g);
         default: break;
     }
     // point operations: plain row views

@@ -230,7 +230,7 @@ __device__ void patch_borders(uint8_t* tile, const StencilParams& p, int bx0, in
     constexpr bool morph = op_is_morph(OP);
     constexpr uint8_t fill = op_is_dilate(OP) ? 0 : 255;
     const int tid = threadIdx.x;
-    const bool left = rx > 0 && bx0 == 0;
+    const bool left = rx > 0 && bx0 <= 0;
     const bool right = rx > 0 && bx0 + kTileBytes + rx * C > p.rowbytes;
     if (left || right) {
         // columns: (row, side, d, ch)
@@ -537,8 +537,151 @@ int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGe
     return DIP_OK;
 }
 
+// =================================================================================================
+// Fused chain: 5x5 Gaussian (filter2D semantics, reflect-101, RNE) followed by 3x3 square erosion
+// (+inf border) in ONE kernel -- BASELINE.json config 5's pipeline at 2 bytes of HBM traffic per pixel
+// instead of 4.  Everything after the source tile stays in registers: a thread computes
+// the Gaussian of its 16-byte column row by row (as the 5x5 kernel above), keeps the result in its
+// packed u16x2 form (value in the high byte of each lane; the low byte is rounding residue, which cannot
+// change which HIGH byte a 16-bit minimum selects), gets the neighbouring columns' edge words with four
+// warp shuffles, takes the horizontal 3-minimum and keeps the vertical 3-window in registers.  Lanes 0
+// and 31 have only one neighbour, so a tile delivers 480 of its 512 byte columns and tiles overlap by
+// one lane; a warp computes R+2 Gaussian rows for R output rows.  No second shared-memory tile, no
+// __syncthreads after the load.
+// =================================================================================================
+template <int C, int R, int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
+    constexpr int kThreads = kWarps * 32;
+    constexpr int TO = kWarps * R;        // output rows per tile
+    constexpr int ROWS = TO + 6;          // source rows per tile (Gaussian rows TO + 2, each needing +-2)
+    constexpr int kOutBytes = kTileBytes - 32;  // 480 output bytes per tile row (lanes 1..30)
+    static_assert(R % 15 == 0, "R must be a multiple of both register-window periods (5 and 3)");
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* tile = smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + ROWS * kRowBytes);
+
+    const int tx = blockIdx.x, ty = blockIdx.y, f = blockIdx.z;
+    const int gx0 = tx * kOutBytes - 16;  // first byte column of the tile's 512-byte region
+    const int y0 = p.out_y0 + ty * TO;    // first output row
+    const int ytop = y0 - 3;              // source row held by tile row 0
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar, ROWS * kRowBytes);
+    }
+    pdl_wait();
+    if (threadIdx.x == 0) tma_load_3d(tile, &tmap, bar, (gx0 - kHalo) / 4, ytop, f);
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const bool border = gx0 <= 0 || gx0 + kTileBytes + 2 * C > p.rowbytes || ytop < p.valid_y0 || ytop + ROWS > p.valid_y1;
+    if (border) {
+        __syncthreads();
+        patch_borders<kConv5, C, ROWS, kThreads>(tile, p, gx0, ytop);
+    }
+
+    const int cx = gx0 + 16 * lane;       // first byte of this thread's column
+    const int yw = y0 + warp * R;         // first output row of this warp
+    if (yw >= p.out_y1) return;           // whole warp
+    const int n_out = min(R, p.out_y1 - yw);
+    // Gaussian bytes outside [0, rowbytes) count as 255 for the erosion: per-lane masks in packed form
+    uint32_t colmask[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int b0 = cx + 4 * j;
+        auto out = [&](int pos) { return (pos < 0 || pos >= p.rowbytes) ? 0xFF00u : 0u; };
+        colmask[2 * j] = out(b0) | (out(b0 + 2) << 16);
+        colmask[2 * j + 1] = out(b0 + 1) | (out(b0 + 3) << 16);
+    }
+    const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // source row yw - 3
+    const bool store_lane = lane != 0 && lane != 31 && cx < ((p.rowbytes + 15) & ~15);
+    uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
+
+    Acc8 h0, h1, h2, h3, h4;  // horizontal Gaussian passes of five consecutive source rows
+    Acc8 m0, m1;              // horizontal minima of the two previous Gaussian rows
+    Row8 row;
+    auto hpass = [&](const uint8_t* rp, Acc8& h) {
+        load_row(rp, row);
+        hsum5<C, 0u>(row, h);
+    };
+    // Gaussian row g (image row yw - 1 + g) from the window, then its horizontal 3-minimum
+    auto gauss_hmin = [&](int g, Acc8& hm) {
+        const int yg = yw - 1 + g;
+        const uint32_t rowmask = (yg >= p.valid_y0 && yg < p.valid_y1) ? 0u : 0xFF00FF00u;
+        Row8 gr;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t v = rne_finish((h0.v[k] + h4.v[k] + 0x007F007Fu) + 4u * (h1.v[k] + h3.v[k]) + 6u * h2.v[k]) | colmask[k] | rowmask;
+            if (k & 1) gr.o[2 + (k >> 1)] = v; else gr.e[2 + (k >> 1)] = v;
+        }
+        gr.e[1] = __shfl_up_sync(0xFFFFFFFFu, gr.e[5], 1);
+        gr.o[1] = __shfl_up_sync(0xFFFFFFFFu, gr.o[5], 1);
+        gr.e[6] = __shfl_down_sync(0xFFFFFFFFu, gr.e[2], 1);
+        gr.o[6] = __shfl_down_sync(0xFFFFFFFFu, gr.o[2], 1);
+        gr.e[0] = gr.o[0] = gr.e[7] = gr.o[7] = 0u;  // outside a 3-tap's reach
+        hmnmx3<C, false>(gr, hm);
+    };
+    hpass(colp, h0);
+    hpass(colp + kRowBytes, h1);
+    hpass(colp + 2 * kRowBytes, h2);
+    hpass(colp + 3 * kRowBytes, h3);
+    hpass(colp + 4 * kRowBytes, h4);
+    gauss_hmin(0, m0);
+    h0 = h1; h1 = h2; h2 = h3; h3 = h4;
+    hpass(colp + 5 * kRowBytes, h4);
+    gauss_hmin(1, m1);
+    h0 = h1; h1 = h2; h2 = h3; h3 = h4;
+    const int n_loop = (n_out == R) ? R : n_out;
+#pragma unroll 5
+    for (int i = 0; i < n_loop; ++i) {
+        hpass(colp + (i + 6) * kRowBytes, h4);
+        Acc8 m2;
+        gauss_hmin(i + 2, m2);
+        if (store_lane) {
+            uint32_t out[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                out[j] = pack_hi(mnmx3<false>(m0.v[2 * j], m1.v[2 * j], m2.v[2 * j]), mnmx3<false>(m0.v[2 * j + 1], m1.v[2 * j + 1], m2.v[2 * j + 1]));
+            __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch), make_uint4(out[0], out[1], out[2], out[3]));
+        }
+        m0 = m1; m1 = m2;
+        h0 = h1; h1 = h2; h2 = h3; h3 = h4;
+    }
+}
+
+template <int C, int R, int kWarps>
+int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
+    constexpr int TO = kWarps * R, ROWS = TO + 6;
+    constexpr int smem_bytes = ROWS * kRowBytes + 16;
+    const CUtensorMap* map = nullptr;
+    int rc = get_tmap(ctx, const_cast<dip_image*>(src), kBoxWords, ROWS, &map);
+    if (rc != DIP_OK) return rc;
+    StencilParams p{};
+    p.dst = dst->v;
+    p.rowbytes = src->v.rowbytes;
+    p.width = src->v.width;
+    p.valid_y0 = g.valid_y0; p.valid_y1 = g.valid_y1;
+    p.out_y0 = g.out_y0; p.out_y1 = g.out_y1; p.dst_y0 = g.dst_y0;
+    p.tiles_x = (src->v.rowbytes + (kTileBytes - 32) - 1) / (kTileBytes - 32);
+    p.tiles_y = (g.out_y1 - g.out_y0 + TO - 1) / TO;
+    if (p.tiles_x <= 0 || p.tiles_y <= 0) return DIP_OK;
+    if (p.tiles_y > 65535 || src->v.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
+    static std::atomic<uint64_t> attr_set{0};
+    const uint64_t dev_bit = 1ull << (ctx->device & 63);
+    if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
+        DIP_CUDA(ctx, cudaFuncSetAttribute(fused_g5e3_kernel<C, R, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
+    }
+    DIP_CUDA(ctx, launch_kernel(fused_g5e3_kernel<C, R, kWarps>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
+                                dim3(kWarps * 32), smem_bytes, ctx->compute, *map, p));
+    DIP_CHECK_LAUNCH(ctx, "fused_g5e3_kernel");
+    return DIP_OK;
+}
+
 // Development knob (dip_debug_set "tile_rows"): 0 = automatic, 64 or 32 forces the tile height.
-struct Knobs { int tile_rows = 0; };
+struct Knobs { int tile_rows = 0, fused_rows = 0; };
 Knobs g_knobs;
 
 template <int OP>
@@ -727,6 +870,18 @@ int stencil_convolve_sep(dip_ctx* ctx, const dip_image* src, dip_image* dst, con
                 "run two dip_convolve passes for other kernels");
 }
 
+int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
+    int rc = check_geom(ctx, src, dst, g);
+    if (rc != DIP_OK) return rc;
+    const bool two = g_knobs.fused_rows == 2;  // development: 2-warp CTAs
+    switch (src->v.channels) {
+        case 1: return two ? launch_fused_g5e3<1, 15, 2>(ctx, src, dst, g) : launch_fused_g5e3<1, 15, 4>(ctx, src, dst, g);
+        case 3: return two ? launch_fused_g5e3<3, 15, 2>(ctx, src, dst, g) : launch_fused_g5e3<3, 15, 4>(ctx, src, dst, g);
+        case 4: return two ? launch_fused_g5e3<4, 15, 2>(ctx, src, dst, g) : launch_fused_g5e3<4, 15, 4>(ctx, src, dst, g);
+    }
+    return fail(ctx, DIP_ERR_ARG, "bad channel count");
+}
+
 int stencil_gaussian3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
     int rc = check_geom(ctx, src, dst, g);
     if (rc != DIP_OK) return rc;
@@ -742,6 +897,7 @@ extern "C" {
 int dip_debug_set(const char* key, int value) {
     if (!key) return fail(nullptr, DIP_ERR_ARG, "null key");
     if (!strcmp(key, "tile_rows")) g_knobs.tile_rows = value;
+    else if (!strcmp(key, "fused_rows")) g_knobs.fused_rows = value;
     else return fail(nullptr, DIP_ERR_ARG, "unknown knob %s", key);
     return DIP_OK;
 }
@@ -785,6 +941,13 @@ int dip_convolve_separable(dip_ctx* ctx, const dip_image* src, dip_image* dst, c
     if (rc != DIP_OK) return rc;
     if ((rc = begin_op(ctx, src, dst)) != DIP_OK) return rc;
     return stencil_convolve_sep(ctx, src, dst, krow, kw, kcol, kh, full_geom(src));
+}
+
+int dip_gauss5x5_erode3x3(dip_ctx* ctx, const dip_image* src, dip_image* dst) {
+    int rc = check_pair(ctx, src, dst, false);
+    if (rc != DIP_OK) return rc;
+    if ((rc = begin_op(ctx, src, dst)) != DIP_OK) return rc;
+    return stencil_gauss5_erode3(ctx, src, dst, full_geom(src));
 }
 
 int dip_gaussian_blur3x3(dip_ctx* ctx, const dip_image* src, dip_image* dst) {

@@ -19,10 +19,12 @@ from . import shard
 
 
 class MosaicBand:
-    def __init__(self, ctx, width: int, total_rows: int, world: int, rank: int, radii=(2, 1)):
+    def __init__(self, ctx, width: int, total_rows: int, world: int, rank: int, radii=(2, 1), fused: bool = False):
+        """fused=True runs the chain as ONE kernel (dip_gauss5x5_erode3x3, halo 3): half the HBM traffic."""
         self.ctx = ctx
         self.width, self.total_rows, self.world, self.rank = width, total_rows, world, rank
-        self.radii = list(radii)
+        self.fused = fused
+        self.radii = [3] if fused else list(radii)
         self.halo = shard.chain_halo(self.radii)
         self.band = shard.mosaic_band(total_rows, world, rank, self.halo)
         b = self.band
@@ -32,7 +34,7 @@ class MosaicBand:
         self.below = None
         self._imported = []  # IPC-mapped images this band opened (closed with it)
         ops = {p: op for _, p, op in ctx.reference_ops()}
-        self.chain = [ops["convolution-gaussian-blur-5x5"], ops["erosion-square"]][: len(self.radii)]
+        self.chain = [ctx.fused_chain_op()] if fused else [ops["convolution-gaussian-blur-5x5"], ops["erosion-square"]][: len(self.radii)]
 
     # -- setup ---------------------------------------------------------------------------------
     def fill_synthetic(self, seed: int = 0):

@@ -221,6 +221,15 @@ class Context:
     def gaussian_blur3x3(self, src: Image, dst: Image):
         check(lib().dip_gaussian_blur3x3(self._h, src._h, dst._h), self._h)
 
+    def gauss5x5_erode3x3(self, src: Image, dst: Image):
+        """Fused chain: 5x5 Gaussian convolution then 3x3 square erosion in one kernel."""
+        check(lib().dip_gauss5x5_erode3x3(self._h, src._h, dst._h), self._h)
+
+    def fused_chain_op(self) -> capi.Op:
+        op = capi.Op()
+        op.kind = 10  # DIP_OP_GAUSS5X5_ERODE3X3
+        return op
+
     # -- the reference's list as data --------------------------------------------------------
     def reference_ops(self):
         """[(description, prefix, Op)] for the 12 device operations, opencv/benchmark.py:94-105."""

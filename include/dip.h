@@ -156,6 +156,11 @@ DIP_API int dip_convolve_separable(dip_ctx* ctx, const dip_image* src, dip_image
  * fixed-point blur: [1 2 1]x[1 2 1]/16 rounded half-up, BORDER_REFLECT_101. */
 DIP_API int dip_gaussian_blur3x3(dip_ctx* ctx, const dip_image* src, dip_image* dst);
 
+/* Fused chain (SURVEY.md 8f rank 4 / BASELINE.json config 5): dst = erode3x3_square(filter2D(src, 5x5 Gaussian))
+ * in one kernel -- each pixel crosses HBM once in and once out.  Same result, bit for bit, as
+ * dip_convolve(5x5 Gaussian) followed by dip_erode(3x3 ones) (opencv:103 then opencv:99). */
+DIP_API int dip_gauss5x5_erode3x3(dip_ctx* ctx, const dip_image* src, dip_image* dst);
+
 /* ---- the reference's operation list as data (opencv:92-105, sycl:331-358) ---------- */
 typedef enum dip_op_kind {
     DIP_OP_COPY = 0,
@@ -167,7 +172,8 @@ typedef enum dip_op_kind {
     DIP_OP_CONVOLVE = 6,
     DIP_OP_CONVOLVE_SEPARABLE = 7,
     DIP_OP_GAUSSIAN_BLUR3X3 = 8,
-    DIP_OP_DILATE = 9
+    DIP_OP_DILATE = 9,
+    DIP_OP_GAUSS5X5_ERODE3X3 = 10
 } dip_op_kind;
 
 typedef struct dip_op {
@@ -265,7 +271,7 @@ DIP_API int dip_apply_rows(dip_ctx* ctx, const dip_op* op, const dip_image* src,
                            int dst_row0);
 
 /* ---- development hook: kernel-selection knobs for A/B measurements inside one process.
- * keys: "tile_rows" (stencil tile height: 0 = automatic, 64 or 32).  Not needed by applications. */
+ * keys: "tile_rows" (stencil tile height: 0 = automatic, 60 or 32), "fused_rows" (fused chain: 0 = 4-warp CTAs, 2 = 2-warp CTAs).  Not needed by applications. */
 DIP_API int dip_debug_set(const char* key, int value);
 
 #ifdef __cplusplus

@@ -431,3 +431,42 @@ def test_native_cli_driver_jpeg_through_nvjpeg(ctx, dip, orc, tmp_path):
         psnr = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
         # threshold output is a hard 0/255 image of a noisy channel: JPEG ringing and decoder differences flip pixels
         assert psnr > (18.0 if prefix == "threshold" else 30.0), (prefix, psnr)
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_fused_gauss5x5_erode3x3_equals_the_two_ops(ctx, dip, orc, c):
+    """dip_gauss5x5_erode3x3 (one kernel) == filter2D 5x5 then erode 3x3 (opencv:103 then :99), bit for bit."""
+    rng = np.random.default_rng(70 + c)
+    for (h, w) in [(1, 1), (2, 2), (3, 7), (1, 40), (40, 1), (33, 47), (57, 160), (58, 161), (59, 481), (117, 500), (200, 1031)]:
+        img = rand_img(rng, h, w, c)
+        want = orc.erode(orc.filter2d(img, orc.BLUR_5X5), orc.SQUARE_MASK)
+        for knob in (0, 2):
+            dip.lib().dip_debug_set(b"fused_rows", knob)
+            got = run_op(ctx, "gauss5x5_erode3x3", (), img)
+            assert np.array_equal(got, want), f"{h}x{w}x{c} fused_rows={knob}: {(got != want).sum()} bytes differ"
+    dip.lib().dip_debug_set(b"fused_rows", 0)
+    stack = rng.integers(0, 256, (3, 70, 333, c), dtype=np.uint8)
+    got = run_op(ctx, "gauss5x5_erode3x3", (), stack)
+    for f in range(3):
+        assert np.array_equal(got[f], orc.erode(orc.filter2d(stack[f], orc.BLUR_5X5), orc.SQUARE_MASK))
+
+
+def test_mosaic_fused_chain_known_answers(ctx, dip):
+    """The fused single-kernel chain on row bands with pulled halos reproduces the oracle's mosaic checksums."""
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "mosaic_kat.json")) as f:
+        kat = json.load(f)
+    for side_s, want in sorted(kat.items(), key=lambda kv: int(kv[0])):
+        side = int(side_s)
+        for world in ((1, 3, 8) if side < 65536 else (1,)):
+            bands = [dip.mosaic.MosaicBand(ctx, side, side, world, r, fused=True) for r in range(world)]
+            for b in bands:
+                b.fill_synthetic(seed=0)
+            for b in bands:
+                b.connect_local(bands)
+            for b in bands:
+                b.step()
+            got = sum(b.checksum() for b in bands) & 0xFFFFFFFFFFFFFFFF
+            for b in bands:
+                b.close()
+            assert f"{got:016x}" == want, (side, world)
