@@ -115,8 +115,25 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
 }
 
 // ---- packed u16x2 helpers -------------------------------------------------------------------
-__device__ __forceinline__ uint32_t even_bytes(uint32_t w) { return __byte_perm(w, 0u, 0x4240); }  // (b0, b2)
-__device__ __forceinline__ uint32_t odd_bytes(uint32_t w) { return __byte_perm(w, 0u, 0x4341); }   // (b1, b3)
+// Pipe balancing.  On sm_100 the integer ALU pipe (PRMT, LOP3, SHF, LEA, IADD3, VIMNMX) and the FMA pipe
+// (IMAD) each accept one warp instruction every 2 cycles per scheduler and issue in parallel
+// (tools/ubench/int_pipes.cu: 0.51 / 0.51 / 0.98 instr/clk alone / alone / mixed 1:1; IMAD.HI is 0.26).
+// The 5-tap and fused 3-tap kernels are ALU-pipe bound, so work that can be phrased as a multiply-add is
+// phrased that way: additions as a*1+b with the 1 read from constant memory (ptxas cannot fold it and
+// emits IMAD), and the even-byte unpack as w - 256*odd instead of a second PRMT.
+// A constant the compiler must keep in a register (so that `x * imm + K` is ONE IMAD with K as its addend
+// instead of a shift plus an ALU-pipe add).  Call once, outside the row loop.
+template <uint32_t V>
+__device__ __forceinline__ uint32_t reg_const() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %1;" : "=r"(r) : "n"(V));
+    return r;
+}
+__constant__ uint32_t c_one = 1u;
+__device__ __forceinline__ uint32_t padd(uint32_t a, uint32_t b) { return a * c_one + b; }  // add on the FMA pipe
+
+__device__ __forceinline__ uint32_t odd_bytes(uint32_t w) { return __byte_perm(w, 0u, 0x4341); }   // (b1, b3): PRMT
+__device__ __forceinline__ uint32_t even_bytes(uint32_t w, uint32_t odd) { return w - odd * 256u; } // (b0, b2): IMAD
 __device__ __forceinline__ uint32_t funnel16(uint32_t lo, uint32_t hi) { return __byte_perm(lo, hi, 0x5432); }
 
 // A row of 8 words (2 halo, 4 own, 2 halo) unpacked into even / odd byte streams.
@@ -152,23 +169,23 @@ struct Acc8 {
 };
 
 // horizontal [1 2 1] (sum <= 1020 per lane) plus a per-lane rounding bias folded into the first add
-template <int C, uint32_t BIAS>
-__device__ __forceinline__ void hsum3(const Row8& r, Acc8& h) {
+template <int C>
+__device__ __forceinline__ void hsum3(const Row8& r, Acc8& h, uint32_t bias) {
 #define DIP_H3(j)                                                                                     \
-    h.v[2 * j] = (pair_at<4 * j - C>(r) + pair_at<4 * j + C>(r) + BIAS) + 2u * r.e[2 + j];            \
-    h.v[2 * j + 1] = (pair_at<4 * j + 1 - C>(r) + pair_at<4 * j + 1 + C>(r) + BIAS) + 2u * r.o[2 + j];
+    h.v[2 * j] = padd(pair_at<4 * j - C>(r), padd(pair_at<4 * j + C>(r), 2u * r.e[2 + j] + bias));    \
+    h.v[2 * j + 1] = padd(pair_at<4 * j + 1 - C>(r), padd(pair_at<4 * j + 1 + C>(r), 2u * r.o[2 + j] + bias));
     DIP_H3(0) DIP_H3(1) DIP_H3(2) DIP_H3(3)
 #undef DIP_H3
 }
 
 // horizontal [1 4 6 4 1] (sum <= 4080 per lane) plus a per-lane rounding bias folded into the first add
-template <int C, uint32_t BIAS>
-__device__ __forceinline__ void hsum5(const Row8& r, Acc8& h) {
+template <int C>
+__device__ __forceinline__ void hsum5(const Row8& r, Acc8& h, uint32_t bias) {
 #define DIP_H5(j)                                                                                     \
-    h.v[2 * j] = (pair_at<4 * j - 2 * C>(r) + pair_at<4 * j + 2 * C>(r) + BIAS) +                     \
-                 4u * (pair_at<4 * j - C>(r) + pair_at<4 * j + C>(r)) + 6u * r.e[2 + j];              \
-    h.v[2 * j + 1] = (pair_at<4 * j + 1 - 2 * C>(r) + pair_at<4 * j + 1 + 2 * C>(r) + BIAS) +         \
-                     4u * (pair_at<4 * j + 1 - C>(r) + pair_at<4 * j + 1 + C>(r)) + 6u * r.o[2 + j];
+    h.v[2 * j] = (pair_at<4 * j - 2 * C>(r) + pair_at<4 * j + 2 * C>(r)) +                            \
+                 (4u * padd(pair_at<4 * j - C>(r), pair_at<4 * j + C>(r)) + (6u * r.e[2 + j] + bias));     \
+    h.v[2 * j + 1] = (pair_at<4 * j + 1 - 2 * C>(r) + pair_at<4 * j + 1 + 2 * C>(r)) +                \
+                     (4u * padd(pair_at<4 * j + 1 - C>(r), pair_at<4 * j + 1 + C>(r)) + (6u * r.o[2 + j] + bias));
     DIP_H5(0) DIP_H5(1) DIP_H5(2) DIP_H5(3)
 #undef DIP_H5
 }
@@ -210,8 +227,8 @@ __device__ __forceinline__ void load_row(const uint8_t* rowp, Row8& r) {
     const uint32_t w[8] = {a.x, a.y, b.x, b.y, b.z, b.w, c.x, c.y};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-        r.e[i] = even_bytes(w[i]);
         r.o[i] = odd_bytes(w[i]);
+        r.e[i] = even_bytes(w[i], r.o[i]);
     }
 }
 
@@ -307,8 +324,8 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
                 for (int j = 0; j < 4; ++j) out[j] = pack_lo(h.v[2 * j], h.v[2 * j + 1]);
             } else {
                 constexpr uint32_t scale = OP == kConvRow3 ? 64u : 16u;  // sum * scale has the result in the high byte
-                if constexpr (OP == kConvRow3) hsum3<C, 0u>(row, h);
-                else hsum5<C, 0u>(row, h);
+                if constexpr (OP == kConvRow3) hsum3<C>(row, h, 0u);
+                else hsum5<C>(row, h, 0u);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     out[j] = pack_hi(rne_finish(h.v[2 * j] * scale + 0x007F007Fu), rne_finish(h.v[2 * j + 1] * scale + 0x007F007Fu));
@@ -323,7 +340,7 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
             const uint4 b = *reinterpret_cast<const uint4*>(rp);
             const uint32_t w[4] = {b.x, b.y, b.z, b.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { a.v[2 * j] = even_bytes(w[j]); a.v[2 * j + 1] = odd_bytes(w[j]); }
+            for (int j = 0; j < 4; ++j) { a.v[2 * j + 1] = odd_bytes(w[j]); a.v[2 * j] = even_bytes(w[j], a.v[2 * j + 1]); }
         };
         load_own(colp, w0);
         load_own(colp + kRowBytes, w1);
@@ -395,11 +412,13 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
         }
     } else if constexpr (op_taps(OP) == 1) {
         // 3-tap Gaussians.  h* hold the horizontal pass of rows i-1, i, i+1.
+        const uint32_t hbias = OP == kConv3Sep ? reg_const<0x00010001u>() : 0u;
+        const uint32_t vbias = reg_const<(OP == kGauss3 ? 0x00800080u : 0x007F007Fu)>();
         Acc8 h0, h1, h2;
         Row8 row;
         auto hpass = [&](const uint8_t* rp, Acc8& h) {
             load_row(rp, row);
-            hsum3<C, OP == kConv3Sep ? 0x00010001u : 0u>(row, h);
+            hsum3<C>(row, h, hbias);
             if constexpr (OP == kConv3Sep) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) h.v[k] = round_keep_scaled<2>(h.v[k]);  // 4 * RNE(sum / 4)
@@ -414,11 +433,11 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 // V = h0 + 2 h1 + h2 <= 4080 (both variants); X = 16 V has the result in the high byte
-                const uint32_t u = h0.v[k] + h2.v[k];
+                const uint32_t u = padd(h0.v[k], h2.v[k]);
                 if constexpr (OP == kGauss3) {
-                    res[k] = u * 16u + h1.v[k] * 32u + 0x00800080u;          // (S + 8) >> 4
+                    res[k] = u * 16u + (h1.v[k] * 32u + vbias);              // (S + 8) >> 4
                 } else {
-                    res[k] = rne_finish(u * 16u + h1.v[k] * 32u + 0x007F007Fu);
+                    res[k] = rne_finish(u * 16u + (h1.v[k] * 32u + vbias));
                 }
             }
             __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch),
@@ -427,11 +446,13 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
         }
     } else {
         // 5-tap Gaussians.  h* hold the horizontal pass of rows i-2 .. i+2.
+        const uint32_t hbias = OP == kConv5Sep ? reg_const<0x00070007u>() : 0u;
+        const uint32_t vbias = reg_const<0x007F007Fu>();
         Acc8 h0, h1, h2, h3, h4;
         Row8 row;
         auto hpass = [&](const uint8_t* rp, Acc8& h) {
             load_row(rp, row);
-            hsum5<C, OP == kConv5Sep ? 0x00070007u : 0u>(row, h);
+            hsum5<C>(row, h, hbias);
             if constexpr (OP == kConv5Sep) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) h.v[k] = round_keep_scaled<4>(h.v[k]);  // 16 * RNE(sum / 16)
@@ -448,7 +469,10 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
                 // X = sum of [1 4 6 4 1] x h <= 65280: result in the high byte after RNE
-                const uint32_t x = (h0.v[k] + h4.v[k] + 0x007F007Fu) + 4u * (h1.v[k] + h3.v[k]) + 6u * h2.v[k];
+                // the separable variant (two roundings) is the most ALU-bound: all of its vertical adds go to the FMA pipe
+                const uint32_t x = OP == kConv5Sep
+                                       ? padd(h0.v[k], padd(h4.v[k], 4u * padd(h1.v[k], h3.v[k]) + (6u * h2.v[k] + vbias)))
+                                       : (h0.v[k] + h4.v[k]) + (4u * padd(h1.v[k], h3.v[k]) + (6u * h2.v[k] + vbias));
                 res[k] = rne_finish(x);
             }
             __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch),
@@ -604,7 +628,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_co
     Row8 row;
     auto hpass = [&](const uint8_t* rp, Acc8& h) {
         load_row(rp, row);
-        hsum5<C, 0u>(row, h);
+        hsum5<C>(row, h, 0u);
     };
     // Gaussian row g (image row yw - 1 + g) from the window, then its horizontal 3-minimum
     auto gauss_hmin = [&](int g, Acc8& hm) {
