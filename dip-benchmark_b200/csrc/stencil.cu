@@ -718,7 +718,8 @@ int launch_tiled_c(dip_ctx* ctx, const dip_image* src, dip_image* dst, const Row
             // late CTAs' loads overlap early CTAs' arithmetic; stacks keep the 64-row tile.
             const long long tiles64 = (long long)((src->v.rowbytes + kTileBytes - 1) / kTileBytes) * ((g.out_y1 - g.out_y0 + 63) / 64) * src->v.frames;
             const bool small = g_knobs.tile_rows ? g_knobs.tile_rows < 60 : tiles64 < 2ll * 6 * ctx->sm_count;
-            constexpr int kSmallR = op_taps(OP) == 2 ? 10 : 9;  // multiples of the window period (5 / 3 rows)
+            // multiples of the window period (5 / 3 rows); measured best for one 3504x2336 image: 40- and 24-row tiles
+            constexpr int kSmallR = op_taps(OP) == 2 ? 10 : 6;
             return small ? launch_tiled<OP, 3, kSmallR, 4>(ctx, src, dst, g) : launch_tiled<OP, 3, 15, 4>(ctx, src, dst, g);
         }
     }
