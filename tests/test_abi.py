@@ -63,3 +63,24 @@ def test_no_device_fails_loudly(dip):
     with pytest.raises(dip.DipError) as e:
         dip.Context(0)
     assert "no CPU fallback" in str(e.value)
+
+
+def test_measure_time_mirrors_the_reference_loop(dip):
+    """benchmark.measure_time = opencv/benchmark.py:26-38: one cold call, then `rounds` calls; optional sync hook."""
+    from dip_benchmark_b200 import benchmark
+    calls, syncs = [], []
+    once, avg = benchmark.measure_time(lambda: calls.append(1), 7, lambda: syncs.append(1))
+    assert len(calls) == 8 and len(syncs) == 2 and once >= 0 and avg >= 0
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference runs here on the CPU (OpenCV path or the C port) and prints exactly one JSON line."""
+    import json
+    import sys
+    out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                                   "--cpu-frames", "1"], text=True)
+    lines = [l for l in out.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "Mpixel/s" and d["cpu_baseline"]["kind"] in ("reference", "port")
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0

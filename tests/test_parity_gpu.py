@@ -470,3 +470,48 @@ def test_mosaic_fused_chain_known_answers(ctx, dip):
             for b in bands:
                 b.close()
             assert f"{got:016x}" == want, (side, world)
+
+
+def test_external_stream_registered_memory_and_device_info(ctx, dip):
+    """The remaining entry points of include/dip.h: dip_init_on_stream, dip_host_register/unregister,
+    dip_get_device_info, dip_device_count, dip_version, dip_flush_l2."""
+    import ctypes as C
+    L = dip.lib()
+    n = C.c_int()
+    assert L.dip_device_count(C.byref(n)) == 0 and n.value >= 1
+    assert b"sm_100a" in L.dip_version()
+    info = ctx.device_info()
+    assert info["cc"][0] >= 10 and info["sm_count"] >= 100 and info["l2_bytes"] > 0
+    ctx.flush_l2(); ctx.sync()
+    # a context on a caller-owned stream (created through the CUDA runtime the library links statically is not
+    # reachable from here, so use cuda-python's runtime binding when present)
+    try:
+        from cuda.bindings import runtime as rt
+    except Exception:  # noqa: BLE001
+        rt = None
+    if rt is not None:
+        err, stream = rt.cudaStreamCreate()
+        assert int(err) == 0
+        h = C.c_void_p()
+        assert L.dip_init_on_stream(C.byref(h), 0, C.c_void_p(int(stream))) == 0
+        img = np.arange(64 * 48 * 3, dtype=np.uint32).astype(np.uint8).reshape(48, 64, 3)
+        a, b = C.c_void_p(), C.c_void_p()
+        assert L.dip_image_create(h, 64, 48, 3, C.byref(a)) == 0 and L.dip_image_create(h, 64, 48, 3, C.byref(b)) == 0
+        assert L.dip_upload(h, a, img.ctypes.data, 0) == 0
+        assert L.dip_invert(h, a, b) == 0
+        out = np.empty_like(img)
+        assert L.dip_download(h, b, out.ctypes.data, 0) == 0 and L.dip_sync(h) == 0
+        assert np.array_equal(out, 255 - img)
+        L.dip_image_destroy(a); L.dip_image_destroy(b); L.dip_shutdown(h)
+        rt.cudaStreamDestroy(stream)
+    # registered (page-locked in place) numpy memory takes the single-copy path
+    buf = np.random.default_rng(1).integers(0, 256, (256, 1024, 3), dtype=np.uint8)
+    assert L.dip_host_register(buf.ctypes.data, buf.nbytes) == 0
+    im = ctx.image(1024, 256, 3)
+    im.upload(buf)
+    back = np.empty_like(buf)
+    assert L.dip_host_register(back.ctypes.data, back.nbytes) == 0
+    im.download(back)
+    assert np.array_equal(back, buf)
+    assert L.dip_host_unregister(buf.ctypes.data) == 0 and L.dip_host_unregister(back.ctypes.data) == 0
+    im.close()
