@@ -109,8 +109,11 @@ int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CU
     TmapKey key{};
     key.box_words = box_words;
     key.box_rows = box_rows;
-    // (x in 4-byte words, y, frame): u32 elements lift the 256-element box limit to 1 KiB rows
-    cuuint64_t dims[3] = {(cuuint64_t)(v.pitch / 4), (cuuint64_t)v.height, (cuuint64_t)v.frames};
+    // (x in 4-byte words, y, frame): u32 elements lift the 256-element box limit to 1 KiB rows.  The x extent is
+    // the row's own (16-byte padded) length, not the pitch: a wrapped region of interest must never be read past
+    // its right edge (TMA zero-fills there and the border patch supplies the halo).
+    const size_t row_padded = std::min<size_t>(((size_t)v.rowbytes + 15) & ~(size_t)15, v.pitch);
+    cuuint64_t dims[3] = {(cuuint64_t)(row_padded / 4), (cuuint64_t)v.height, (cuuint64_t)v.frames};
     cuuint64_t strides[2] = {(cuuint64_t)v.pitch, (cuuint64_t)(v.frames > 1 ? v.frame_stride : v.pitch * (size_t)v.height)};
     if (strides[1] == 0) strides[1] = 16;
     cuuint32_t box[3] = {(cuuint32_t)box_words, (cuuint32_t)box_rows, 1};

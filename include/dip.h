@@ -271,7 +271,7 @@ DIP_API int dip_apply_rows(dip_ctx* ctx, const dip_op* op, const dip_image* src,
                            int dst_row0);
 
 /* ---- development hook: kernel-selection knobs for A/B measurements inside one process.
- * keys: "tile_rows" (stencil tile height: 0 = automatic, 60 or 32), "fused_rows" (fused chain: 0 = 4-warp CTAs, 2 = 2-warp CTAs).  Not needed by applications. */
+ * keys: "tile_rows" (stencil tile height: 0 = automatic, 60 = stack tiles, 32 = single-image tiles), "fused_rows" (fused chain: 0 = 4-warp CTAs, 2 = 2-warp CTAs).  Not needed by applications. */
 DIP_API int dip_debug_set(const char* key, int value);
 
 #ifdef __cplusplus
