@@ -122,6 +122,19 @@ cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
 }
 
 #ifdef __CUDACC__
+// 16-byte result store.  Library-owned images pad every row to 16 bytes, so the last vector of a row may spill
+// into the padding; a wrapped region of interest has real pixels there, so only `valid` bytes are written.
+__device__ __forceinline__ void store16(uint8_t* p, const uint4& v, int valid) {
+    if (valid >= 16) {
+        __stcs(reinterpret_cast<uint4*>(p), v);
+    } else {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int i = 0; i < valid; ++i) p[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+    }
+}
+// bytes of the 16-byte chunk starting at byte `cx` of a row that may be written
+__device__ __forceinline__ int chunk_valid(int cx, int rowbytes, bool exact) { return exact ? rowbytes - cx : 16; }
+
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
@@ -168,6 +181,9 @@ inline dip_image* root_of(dip_image* im) {
     while (im && im->parent) im = im->parent;
     return im;
 }
+
+// true when the bytes between the end of a row and the next 16-byte boundary do NOT belong to the image
+inline bool exact_rows(const ImgView& v) { return v.pitch != (((size_t)v.rowbytes + 15) & ~(size_t)15); }
 
 inline RowGeom full_geom(const dip_image* src) {
     return RowGeom{0, src->v.height, 0, src->v.height, 0};

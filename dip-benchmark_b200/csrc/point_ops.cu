@@ -94,12 +94,23 @@ __global__ void __launch_bounds__(kThreads) point_rows_kernel(ImgView src, ImgVi
     const int vx = (int)(i - row * (size_t)vec_per_row);
     const size_t f = row / (size_t)src.height;
     const size_t y = row - f * (size_t)src.height;
-    const uint4* s = reinterpret_cast<const uint4*>(src.base + f * src.frame_stride + y * src.pitch) + vx;
-    uint4* d = reinterpret_cast<uint4*>(dst.base + f * dst.frame_stride + y * dst.pitch) + vx;
-    *d = point_vec<OP>(*s, t4, m4);
+    // strided layouts are wrapped memory: neither read nor write past the row's last byte
+    const uint8_t* s = src.base + f * src.frame_stride + y * src.pitch + 16 * vx;
+    uint8_t* d = dst.base + f * dst.frame_stride + y * dst.pitch + 16 * vx;
+    const int valid = min(16, src.rowbytes - 16 * vx);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (valid >= 16) {
+        v = *reinterpret_cast<const uint4*>(s);
+    } else {
+        uint32_t w[4] = {0, 0, 0, 0};
+        for (int i = 0; i < valid; ++i) w[i >> 2] |= (uint32_t)s[i] << (8 * (i & 3));
+        v = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    store16(d, point_vec<OP>(v, t4, m4), valid);
 }
 
 // BGR grayscale: a thread converts one 48-byte group = 16 pixels = 3 vectors.
+template <bool exact>  // exact: rows are not padded to 16 bytes (wrapped regions of interest)
 __global__ void __launch_bounds__(kThreads) gray3_kernel(ImgView src, ImgView dst, int groups_per_row, size_t total) {
     pdl_launch_dependents();
     pdl_wait();
@@ -119,7 +130,16 @@ __global__ void __launch_bounds__(kThreads) gray3_kernel(ImgView src, ImgView ds
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
         uint4 v = make_uint4(0, 0, 0, 0);
-        if (j < nv) v = __ldg(reinterpret_cast<const uint4*>(srow + off) + j);
+        if (j < nv) {
+            const int valid = exact ? src.rowbytes - (off + 16 * j) : 16;
+            if (valid >= 16) {
+                v = __ldg(reinterpret_cast<const uint4*>(srow + off) + j);
+            } else {  // wrapped region of interest: do not read past the row
+                uint32_t t[4] = {0, 0, 0, 0};
+                for (int i = 0; i < valid; ++i) t[i >> 2] |= (uint32_t)srow[off + 16 * j + i] << (8 * (i & 3));
+                v = make_uint4(t[0], t[1], t[2], t[3]);
+            }
+        }
         w[4 * j + 0] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
     }
     uint32_t o[12];
@@ -136,7 +156,7 @@ __global__ void __launch_bounds__(kThreads) gray3_kernel(ImgView src, ImgView ds
     }
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-        if (j < nv) __stcs(reinterpret_cast<uint4*>(drow + off) + j, make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]));
+        if (j < nv) store16(drow + off + 16 * j, make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]), chunk_valid(off + 16 * j, src.rowbytes, exact));
 }
 
 // Same integer mix as oracle/dip_oracle.c:orc_mix32 (kept in sync by tests/test_parity_gpu.py).
@@ -171,7 +191,8 @@ __global__ void __launch_bounds__(kThreads) synth_kernel(ImgView dst, uint32_t s
         }
         w[k] = word;
     }
-    *(reinterpret_cast<uint4*>(dst.base + f * dst.frame_stride + y * dst.pitch) + vx) = make_uint4(w[0], w[1], w[2], w[3]);
+    store16(dst.base + f * dst.frame_stride + y * dst.pitch + 16 * vx, make_uint4(w[0], w[1], w[2], w[3]),
+            chunk_valid(16 * vx, dst.rowbytes, dst.pitch != (((size_t)dst.rowbytes + 15) & ~(size_t)15)));
 }
 
 __global__ void __launch_bounds__(kThreads) checksum_kernel(ImgView src, int vec_per_row, size_t vec_per_frame, uint64_t first_row,
@@ -257,7 +278,10 @@ int launch_grayscale(dip_ctx* ctx, const ImgView& src, const ImgView& dst) {
     const size_t total = (size_t)groups * (size_t)src.height * (size_t)src.frames;
     const size_t blocks = (total + kThreads - 1) / kThreads;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-    DIP_CUDA(ctx, launch_kernel(gray3_kernel, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total));
+    if (exact_rows(src) || exact_rows(dst))
+        DIP_CUDA(ctx, launch_kernel(gray3_kernel<true>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total));
+    else
+        DIP_CUDA(ctx, launch_kernel(gray3_kernel<false>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total));
     DIP_CHECK_LAUNCH(ctx, "gray3_kernel");
     return DIP_OK;
 }

@@ -80,6 +80,7 @@ struct StencilParams {
     int out_y0, out_y1;      // rows to produce (source row coordinates)
     int dst_y0;              // dst row receiving out_y0
     int tiles_x, tiles_y;
+    bool dst_exact;          // dst rows are not padded to 16 bytes (wrapped region of interest)
 };
 
 // ---- PTX wrappers ---------------------------------------------------------------------------
@@ -308,8 +309,9 @@ __device__ void patch_borders(uint8_t* tile, const StencilParams& p, int bx0, in
 // FULL = the band has all R rows (compile-time trip count: the row loops unroll by the period of the
 // register window without a remainder loop); otherwise `nrows_rt` rows.
 template <int OP, int C, int R, bool FULL>
-__device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr, const StencilParams& p, int nrows_rt) {
+__device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr, const StencilParams& p, int nrows_rt, int p_cx) {
     const int nrows = FULL ? R : nrows_rt;
+    const int valid = p.dst_exact ? p.rowbytes - p_cx : 16;  // bytes of this thread's 16-byte chunk that may be stored
     if constexpr (op_is_row_only(OP)) {
         // one-dimensional pass along x: no vertical window
         Row8 row;
@@ -330,7 +332,7 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
                 for (int j = 0; j < 4; ++j)
                     out[j] = pack_hi(rne_finish(h.v[2 * j] * scale + 0x007F007Fu), rne_finish(h.v[2 * j + 1] * scale + 0x007F007Fu));
             }
-            __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch), make_uint4(out[0], out[1], out[2], out[3]));
+            store16(dptr + (size_t)i * p.dst.pitch, make_uint4(out[0], out[1], out[2], out[3]), valid);
         }
     } else if constexpr (op_is_col_only(OP)) {
         // one-dimensional pass along y: only the thread's own 4 words, vertical window of raw rows
@@ -366,7 +368,7 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
             uint4 o;
             if constexpr (op_is_morph(OP)) o = make_uint4(pack_lo(res[0], res[1]), pack_lo(res[2], res[3]), pack_lo(res[4], res[5]), pack_lo(res[6], res[7]));
             else o = make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7]));
-            __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch), o);
+            store16(dptr + (size_t)i * p.dst.pitch, o, valid);
         }
     } else if constexpr (op_is_morph(OP)) {
         constexpr bool MAX = op_is_dilate(OP);
@@ -408,7 +410,7 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
                 h0 = h1;
             }
             h1 = h2;
-            __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch), make_uint4(out[0], out[1], out[2], out[3]));
+            store16(dptr + (size_t)i * p.dst.pitch, make_uint4(out[0], out[1], out[2], out[3]), valid);
         }
     } else if constexpr (op_taps(OP) == 1) {
         // 3-tap Gaussians.  h* hold the horizontal pass of rows i-1, i, i+1.
@@ -440,8 +442,8 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
                     res[k] = rne_finish(u * 16u + (h1.v[k] * 32u + vbias));
                 }
             }
-            __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch),
-                   make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7])));
+            store16(dptr + (size_t)i * p.dst.pitch,
+                    make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7])), valid);
             h0 = h1; h1 = h2;
         }
     } else {
@@ -475,8 +477,8 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
                                        : (h0.v[k] + h4.v[k]) + (4u * padd(h1.v[k], h3.v[k]) + (6u * h2.v[k] + vbias));
                 res[k] = rne_finish(x);
             }
-            __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch),
-                   make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7])));
+            store16(dptr + (size_t)i * p.dst.pitch,
+                    make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7])), valid);
             h0 = h1; h1 = h2; h2 = h3; h3 = h4;
         }
     }
@@ -526,8 +528,8 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
     const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // tile row of source row yw - r
     uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
 
-    if (nrows == R) compute_band<OP, C, R, true>(colp, dptr, p, R);
-    else compute_band<OP, C, R, false>(colp, dptr, p, nrows);
+    if (nrows == R) compute_band<OP, C, R, true>(colp, dptr, p, R, cx);
+    else compute_band<OP, C, R, false>(colp, dptr, p, nrows, cx);
 }
 
 template <int OP, int C, int R, int kWarps>
@@ -548,6 +550,7 @@ int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGe
     p.out_y0 = g.out_y0; p.out_y1 = g.out_y1; p.dst_y0 = g.dst_y0;
     p.tiles_x = (src->v.rowbytes + kTileBytes - 1) / kTileBytes;
     p.tiles_y = (g.out_y1 - g.out_y0 + TH - 1) / TH;
+    p.dst_exact = exact_rows(dst->v);
     if (p.tiles_x <= 0 || p.tiles_y <= 0) return DIP_OK;
     if (p.tiles_y > 65535 || src->v.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
     static std::atomic<uint64_t> attr_set{0};  // per instantiation, one bit per device
@@ -621,6 +624,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_co
     }
     const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // source row yw - 3
     const bool store_lane = lane != 0 && lane != 31 && cx < ((p.rowbytes + 15) & ~15);
+    const int valid = p.dst_exact ? p.rowbytes - cx : 16;
     uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
 
     Acc8 h0, h1, h2, h3, h4;  // horizontal Gaussian passes of five consecutive source rows
@@ -668,7 +672,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_co
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 out[j] = pack_hi(mnmx3<false>(m0.v[2 * j], m1.v[2 * j], m2.v[2 * j]), mnmx3<false>(m0.v[2 * j + 1], m1.v[2 * j + 1], m2.v[2 * j + 1]));
-            __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch), make_uint4(out[0], out[1], out[2], out[3]));
+            store16(dptr + (size_t)i * p.dst.pitch, make_uint4(out[0], out[1], out[2], out[3]), valid);
         }
         m0 = m1; m1 = m2;
         h0 = h1; h1 = h2; h2 = h3; h3 = h4;
@@ -690,6 +694,7 @@ int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const 
     p.out_y0 = g.out_y0; p.out_y1 = g.out_y1; p.dst_y0 = g.dst_y0;
     p.tiles_x = (src->v.rowbytes + (kTileBytes - 32) - 1) / (kTileBytes - 32);
     p.tiles_y = (g.out_y1 - g.out_y0 + TO - 1) / TO;
+    p.dst_exact = exact_rows(dst->v);
     if (p.tiles_x <= 0 || p.tiles_y <= 0) return DIP_OK;
     if (p.tiles_y > 65535 || src->v.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
     static std::atomic<uint64_t> attr_set{0};

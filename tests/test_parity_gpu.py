@@ -381,13 +381,19 @@ def test_wrapped_regions_of_interest_with_foreign_pitch(ctx, dip, orc):
         w, h, y0 = 333, 61, 7
         roi = big[y0:y0 + h, x0:x0 + w]
         src = ctx.wrap(parent.device_ptr + y0 * parent.pitch + x0 * c, w, h, c, pitch=parent.pitch, keepalive=parent)
-        outbig = ctx.image(700, 80, c)      # destination region inside another image with another pitch
+        sentinel = np.full((80, 700, c), 0xAB, np.uint8)
+        outbig = ctx.from_array(sentinel)   # destination region inside another image with another pitch
         dst = ctx.wrap(outbig.device_ptr + 3 * outbig.pitch + 48, w, h, c, pitch=outbig.pitch, keepalive=outbig)  # 48 bytes in
-        for (prefix, name, args), (_, ofn) in zip(dip.REFERENCE_OPS, orc.OPERATIONS):
+        for (prefix, name, args), (_, ofn) in zip(list(dip.REFERENCE_OPS) + [("fused", "gauss5x5_erode3x3", ())],
+                                                  list(orc.OPERATIONS) + [("fused", lambda im: orc.erode(orc.filter2d(im, orc.BLUR_5X5), orc.SQUARE_MASK))]):
             getattr(ctx, name)(src, dst, *args)
-            full = outbig.download()
-            got = full.reshape(80, -1)[3:3 + h, 48:48 + w * c].reshape(h, w, c)
+            full = outbig.download().reshape(80, -1)
+            got = full[3:3 + h, 48:48 + w * c].reshape(h, w, c)
             assert np.array_equal(got, ofn(roi)), f"{prefix} c={c}"
+            # nothing outside the region may be touched (its rows are not padded to 16 bytes: 333 * c is odd-sized)
+            outside = full.copy()
+            outside[3:3 + h, 48:48 + w * c] = 0xAB
+            assert (outside == 0xAB).all(), f"{prefix} c={c} wrote outside its region"
         src.close(); dst.close(); parent.close(); outbig.close()
 
 
