@@ -192,13 +192,23 @@ def dist_setup(n_gpus: int):
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if world > 1:
-        # NCCL prints its version banner on stdout at NCCL_DEBUG=VERSION; stdout must carry the JSON line only
-        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # NCCL prints its version banner to stdout when the communicator is created (these boxes export
+        # NCCL_DEBUG=VERSION); stdout must carry the JSON line only, so file descriptor 1 points at stderr
+        # until the first collective has run
         import torch
         import torch.distributed as dist
-        torch.cuda.set_device(local)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
         return world, rank, local, dist, torch
     return 1, 0, 0, None, None
 
@@ -380,6 +390,21 @@ def run_mosaic(args) -> None:
         cs_total = sum(parts) & 0xFFFFFFFFFFFFFFFF
     else:
         cs_total = cs
+    # (after the checksum: the copy lands in a result buffer) the same peer path with a LARGE message (a quarter of the neighbour's band into scratch rows of the second
+    # buffer): shows what the NVLink route sustains when it is not latency-bound
+    bulk_gbs = None
+    if world > 1:
+        nb = band.below if band.below is not None else band.above
+        rows_bulk = max(1, min(band.band.rows // 4, 4096))
+        barrier_sync(ctx, dist, torch)
+        for it in range(3):
+            if it == 1:
+                ctx.sync()
+                t0 = time.perf_counter()
+            band.bufs[1].copy_rows_from(nb[0], nb[1]["own0"], band.band.own0, rows_bulk)
+        ctx.sync()
+        bulk_s = (time.perf_counter() - t0) / 2
+        bulk_gbs = max_over_ranks(-rows_bulk * side / bulk_s / 1e9, dist, torch) * -1.0   # min over ranks
     peak, peak_src = measured_peak()
     n_m = side * side
     if rank == 0:
@@ -397,7 +422,8 @@ def run_mosaic(args) -> None:
                          "note": "per GPU: algorithmic bytes of the band (2 x bytes per pass) / step time"},
             "halo": None if world == 1 else {"bytes_per_step_total": halo_bytes, "bytes_per_gpu_per_direction": 3 * side,
                                              "exchange_ms": ex_ms, "achieved_gbs_per_gpu": 2 * 3 * side / (ex_ms / 1e3) / 1e9,
-                                             "nvlink_peak_gbs": 770.0, "note": "196 608-byte messages: latency-bound, not bandwidth-bound"},
+                                             "nvlink_peak_gbs": 770.0, "note": "196 608-byte messages: latency-bound, not bandwidth-bound",
+                                             "bulk_peer_copy_gbs": bulk_gbs, "bulk_note": "same dip_copy_rows path, a quarter band (up to 268 MB) per copy, slowest rank"},
             "checksum": f"{cs_total:016x}",
         }
         print(json.dumps(line))
