@@ -10,7 +10,8 @@ through cv.UMat) and stores
   * kat.json        : sha256[:16] / crc32 of every op's output for the two full-size inputs
                       A = cv2.imread(data/fundus.jpg) and B = default_rng(0),
   * generic_cases.npz : outputs for argument shapes the benchmark does not use (odd masks,
-                      dilate, thresholds, a non-dyadic float kernel).
+                      dilate, thresholds, a non-dyadic float kernel),
+  * pattern_cases.npz : saturated, maximum-gradient and rounding-tie patterns (every .5 case).
 The fixtures travel to the GPU box; /root/reference and this script's cv2 dependency do not
 have to.
 """
@@ -85,6 +86,21 @@ def main() -> None:
     for t, mv in ((0, 255), (127, 255), (200, 99), (255, 255)):
         generic[f"threshold/{t}_{mv}"] = ref.threshold(img, t, mv)
     np.savez_compressed(os.path.join(HERE, "generic_cases.npz"), **generic)
+
+    # saturated / maximum-gradient / rounding-tie patterns (regular, so they compress to a few KB)
+    h, w = 67, 530
+    yy, xx = np.mgrid[0:h, 0:w]
+    pats = {
+        "all255": np.full((h, w), 255), "columns": (xx % 2) * 255, "rows": (yy % 2) * 255, "checker": ((xx + yy) % 2) * 255,
+        "ties8": ((xx * 3 + yy * 5) % 32) * 8, "ties2": ((xx + 2 * yy) % 4) * 2 + 1, "ramp": (xx + yy) % 256,
+    }
+    patterns = {}
+    for name, plane in pats.items():
+        img = np.ascontiguousarray(np.repeat(plane.astype(np.uint8)[:, :, None], 3, axis=2))
+        patterns[f"{name}/input"] = img
+        for prefix, fn in ref.OPERATIONS:
+            patterns[f"{name}/{prefix}"] = fn(img)
+    np.savez_compressed(os.path.join(HERE, "pattern_cases.npz"), **patterns)
 
     kat = {"cv2": cv.__version__, "inputs": {}, "outputs": {}}
     A = cv.imread(os.path.join(ROOT, "data", "fundus.jpg"))

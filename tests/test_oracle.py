@@ -118,3 +118,14 @@ def test_row_addressed_synth_and_checksum_compose(orc):
     assert total == orc.checksum(whole)
     # frame f of a stack starts at global row f * height
     assert np.array_equal(orc.synth(64, 50, 1, seed=3, frame=2), orc.synth_rows(64, 50, 1, 3, 100))
+
+
+def test_pattern_cases_match_reference_outputs(orc):
+    """Saturated / maximum-gradient / rounding-tie patterns: the reference's cv2 outputs (pattern_cases.npz)."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pattern_cases.npz"))
+    names = sorted({k.split("/")[0] for k in g.files})
+    assert len(names) == 7
+    for name in names:
+        img = g[f"{name}/input"]
+        for prefix, fn in orc.OPERATIONS:
+            assert np.array_equal(fn(img), g[f"{name}/{prefix}"]), f"{name} {prefix}"

@@ -521,3 +521,38 @@ def test_external_stream_registered_memory_and_device_info(ctx, dip):
     assert np.array_equal(back, buf)
     assert L.dip_host_unregister(buf.ctypes.data) == 0 and L.dip_host_unregister(back.ctypes.data) == 0
     im.close()
+
+
+@pytest.mark.parametrize("c", [1, 3, 4])
+def test_extreme_and_tie_patterns(ctx, dip, orc, c):
+    """Saturated, zero, maximum-gradient and rounding-tie images: the packed 16-bit lanes must not overflow
+    (5x5 sum reaches 65280) and every half-way case must round like OpenCV (half-to-even / half-up)."""
+    h, w = 67, 530
+    yy, xx = np.mgrid[0:h, 0:w]
+    patterns = {
+        "all255": np.full((h, w, c), 255, np.uint8),
+        "all0": np.zeros((h, w, c), np.uint8),
+        "columns": np.repeat(((xx % 2) * 255).astype(np.uint8)[:, :, None], c, axis=2),
+        "rows": np.repeat(((yy % 2) * 255).astype(np.uint8)[:, :, None], c, axis=2),
+        "checker": np.repeat((((xx + yy) % 2) * 255).astype(np.uint8)[:, :, None], c, axis=2),
+        # values in {0, 8, 16, ...}: [1 2 1]/4 and [1 4 6 4 1]/16 sums land on exact halves very often
+        "ties8": np.repeat((((xx * 3 + yy * 5) % 32) * 8).astype(np.uint8)[:, :, None], c, axis=2),
+        "ties2": np.repeat((((xx + 2 * yy) % 4) * 2 + 1).astype(np.uint8)[:, :, None], c, axis=2),
+        "ramp": np.repeat(((xx + yy) % 256).astype(np.uint8)[:, :, None], c, axis=2),
+    }
+    fused = lambda im: orc.erode(orc.filter2d(im, orc.BLUR_5X5), orc.SQUARE_MASK)  # noqa: E731
+    for pname, img in patterns.items():
+        img = np.ascontiguousarray(img)
+        for (prefix, name, args), (_, ofn) in zip(list(dip.REFERENCE_OPS) + [("fused", "gauss5x5_erode3x3", ())],
+                                                  list(orc.OPERATIONS) + [("fused", fused)]):
+            got = run_op(ctx, name, args, img)
+            assert np.array_equal(got, ofn(img)), f"{pname} {prefix} c={c}: {(got != ofn(img)).sum()} bytes differ"
+
+
+def test_golden_pattern_cases(ctx, dip):
+    """The reference's own outputs for the tie / saturation patterns, committed under tests/golden/."""
+    g = np.load(os.path.join(ROOT, "tests", "golden", "pattern_cases.npz"))
+    for name in sorted({k.split("/")[0] for k in g.files}):
+        img = g[f"{name}/input"]
+        for prefix, mname, args in dip.REFERENCE_OPS:
+            assert np.array_equal(run_op(ctx, mname, args, img), g[f"{name}/{prefix}"]), f"{name} {prefix}"
