@@ -159,6 +159,50 @@ __global__ void __launch_bounds__(kThreads) gray3_kernel(ImgView src, ImgView ds
         if (j < nv) store16(drow + off + 16 * j, make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]), chunk_valid(off + 16 * j, src.rowbytes, exact));
 }
 
+// Dense BGR stacks whose rows are whole 48-byte groups (W % 16 == 0, e.g. 3504): the stack is one flat array of
+// groups.  A CTA moves 256 groups = 12 KB through shared memory so that global loads and stores are perfectly
+// coalesced 16-byte vectors (the direct kernel above reads 48-byte-strided vectors, 3x the L1 wavefronts, which
+// shows once the SM clock drops under the power cap); each thread still converts its own 48-byte group, read from
+// shared memory at a 48-byte stride (12 banks apart: conflict-free for 128-bit accesses).
+__global__ void __launch_bounds__(kThreads) gray3_flat_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t nvec) {
+    __shared__ uint4 stage[kThreads * 3];
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t base = (size_t)blockIdx.x * (kThreads * 3);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const size_t i = base + threadIdx.x + (size_t)j * kThreads;
+        if (i < nvec) stage[threadIdx.x + j * kThreads] = ld_stream(src + i);
+    }
+    __syncthreads();
+    uint32_t w[12];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const uint4 v = stage[threadIdx.x * 3 + j];
+        w[4 * j + 0] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
+    }
+    uint32_t o[12];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        const uint32_t y0 = luma(a, kWLo0, kWHi0);
+        const uint32_t y1 = luma(__byte_perm(a, b, 0x7543), kWLo0, kWHi0);
+        const uint32_t y2 = luma(__byte_perm(b, c, 0x7432), kWLo0, kWHi0);
+        const uint32_t y3 = luma(c, kWLo1, kWHi1);
+        o[3 * q + 0] = y0 * 0x00010101u | (y1 << 24);
+        o[3 * q + 1] = y1 * 0x00000101u | (y2 * 0x01010000u);
+        o[3 * q + 2] = y2 | (y3 * 0x01010100u);
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) stage[threadIdx.x * 3 + j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const size_t i = base + threadIdx.x + (size_t)j * kThreads;
+        if (i < nvec) st_stream(dst + i, stage[threadIdx.x + j * kThreads]);
+    }
+}
+
 // Same integer mix as oracle/dip_oracle.c:orc_mix32 (kept in sync by tests/test_parity_gpu.py).
 __host__ __device__ __forceinline__ uint32_t mix32(uint64_t idx, uint32_t seed) {
     uint32_t x = (uint32_t)idx ^ ((uint32_t)(idx >> 32) * 0x9E3779B9u) ^ (seed * 0x85EBCA6Bu + 0xC2B2AE35u);
@@ -231,6 +275,11 @@ bool dense_pair(const ImgView& a, const ImgView& b) {
     return dense(a) && dense(b);
 }
 
+bool use_direct_gray() {  // development switch: DIP_GRAY_DIRECT=1 keeps the strided-load kernel for A/B runs
+    static const bool v = [] { const char* e = getenv("DIP_GRAY_DIRECT"); return e && e[0] == '1'; }();
+    return v;
+}
+
 template <int OP>
 int launch_point_t(dip_ctx* ctx, const ImgView& src, const ImgView& dst, uint32_t t4, uint32_t m4) {
     if (dense_pair(src, dst)) {
@@ -274,6 +323,15 @@ int launch_point(dip_ctx* ctx, PointOp op, const ImgView& src, const ImgView& ds
 int launch_grayscale(dip_ctx* ctx, const ImgView& src, const ImgView& dst) {
     if (src.channels == 1) return launch_point_t<kCopy>(ctx, src, dst, 0, 0);
     if (src.channels == 4) return launch_point_t<3>(ctx, src, dst, 0, 0);
+    if (dense_pair(src, dst) && src.rowbytes % 48 == 0 && !use_direct_gray()) {
+        const size_t nvec = src.pitch * (size_t)src.height * (size_t)src.frames / 16;
+        const size_t blocks = (nvec + kThreads * 3 - 1) / (kThreads * 3);
+        if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
+        DIP_CUDA(ctx, launch_kernel(gray3_flat_kernel, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute,
+                                    reinterpret_cast<const uint4*>(src.base), reinterpret_cast<uint4*>(dst.base), nvec));
+        DIP_CHECK_LAUNCH(ctx, "gray3_flat_kernel");
+        return DIP_OK;
+    }
     const int groups = (src.width + 15) / 16;
     const size_t total = (size_t)groups * (size_t)src.height * (size_t)src.frames;
     const size_t blocks = (total + kThreads - 1) / kThreads;
