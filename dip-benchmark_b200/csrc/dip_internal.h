@@ -124,13 +124,13 @@ cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
 #ifdef __CUDACC__
 // 16-byte result store.  Library-owned images pad every row to 16 bytes, so the last vector of a row may spill
 // into the padding; a wrapped region of interest has real pixels there, so only `valid` bytes are written.
+static __device__ __noinline__ void store_partial(uint8_t* p, uint32_t x, uint32_t y, uint32_t z, uint32_t w_, int valid) {
+    const uint32_t w[4] = {x, y, z, w_};
+    for (int i = 0; i < valid; ++i) p[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+}
 __device__ __forceinline__ void store16(uint8_t* p, const uint4& v, int valid) {
-    if (valid >= 16) {
-        __stcs(reinterpret_cast<uint4*>(p), v);
-    } else {
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        for (int i = 0; i < valid; ++i) p[i] = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-    }
+    if (valid >= 16) __stcs(reinterpret_cast<uint4*>(p), v);          // the hot path: one predicated vector store
+    else store_partial(p, v.x, v.y, v.z, v.w, valid);                 // out of line: keeps the row loops small
 }
 // bytes of the 16-byte chunk starting at byte `cx` of a row that may be written
 __device__ __forceinline__ int chunk_valid(int cx, int rowbytes, bool exact) { return exact ? rowbytes - cx : 16; }

@@ -308,10 +308,18 @@ __device__ void patch_borders(uint8_t* tile, const StencilParams& p, int bx0, in
 // ---- the arithmetic of one warp band: the thread walks down its 16-byte column --------------------
 // FULL = the band has all R rows (compile-time trip count: the row loops unroll by the period of the
 // register window without a remainder loop); otherwise `nrows_rt` rows.
-template <int OP, int C, int R, bool FULL>
+// CLIP = this warp holds the row's last, partial 16-byte chunk of a destination whose rows are NOT padded (a wrapped
+// region of interest): its stores write only the valid bytes.  Every other warp keeps plain vector stores.
+template <bool CLIP>
+__device__ __forceinline__ void put16(uint8_t* p, const uint4& v, int valid) {
+    if constexpr (CLIP) store16(p, v, valid);
+    else __stcs(reinterpret_cast<uint4*>(p), v);
+}
+
+template <int OP, int C, int R, bool FULL, bool CLIP>
 __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr, const StencilParams& p, int nrows_rt, int p_cx) {
     const int nrows = FULL ? R : nrows_rt;
-    const int valid = p.dst_exact ? p.rowbytes - p_cx : 16;  // bytes of this thread's 16-byte chunk that may be stored
+    const int valid = CLIP ? p.rowbytes - p_cx : 16;  // bytes of this thread's 16-byte chunk that may be stored
     if constexpr (op_is_row_only(OP)) {
         // one-dimensional pass along x: no vertical window
         Row8 row;
@@ -332,7 +340,7 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
                 for (int j = 0; j < 4; ++j)
                     out[j] = pack_hi(rne_finish(h.v[2 * j] * scale + 0x007F007Fu), rne_finish(h.v[2 * j + 1] * scale + 0x007F007Fu));
             }
-            store16(dptr + (size_t)i * p.dst.pitch, make_uint4(out[0], out[1], out[2], out[3]), valid);
+            put16<CLIP>(dptr + (size_t)i * p.dst.pitch, make_uint4(out[0], out[1], out[2], out[3]), valid);
         }
     } else if constexpr (op_is_col_only(OP)) {
         // one-dimensional pass along y: only the thread's own 4 words, vertical window of raw rows
@@ -368,7 +376,7 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
             uint4 o;
             if constexpr (op_is_morph(OP)) o = make_uint4(pack_lo(res[0], res[1]), pack_lo(res[2], res[3]), pack_lo(res[4], res[5]), pack_lo(res[6], res[7]));
             else o = make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7]));
-            store16(dptr + (size_t)i * p.dst.pitch, o, valid);
+            put16<CLIP>(dptr + (size_t)i * p.dst.pitch, o, valid);
         }
     } else if constexpr (op_is_morph(OP)) {
         constexpr bool MAX = op_is_dilate(OP);
@@ -410,7 +418,7 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
                 h0 = h1;
             }
             h1 = h2;
-            store16(dptr + (size_t)i * p.dst.pitch, make_uint4(out[0], out[1], out[2], out[3]), valid);
+            put16<CLIP>(dptr + (size_t)i * p.dst.pitch, make_uint4(out[0], out[1], out[2], out[3]), valid);
         }
     } else if constexpr (op_taps(OP) == 1) {
         // 3-tap Gaussians.  h* hold the horizontal pass of rows i-1, i, i+1.
@@ -442,7 +450,7 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
                     res[k] = rne_finish(u * 16u + (h1.v[k] * 32u + vbias));
                 }
             }
-            store16(dptr + (size_t)i * p.dst.pitch,
+            put16<CLIP>(dptr + (size_t)i * p.dst.pitch,
                     make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7])), valid);
             h0 = h1; h1 = h2;
         }
@@ -477,7 +485,7 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
                                        : (h0.v[k] + h4.v[k]) + (4u * padd(h1.v[k], h3.v[k]) + (6u * h2.v[k] + vbias));
                 res[k] = rne_finish(x);
             }
-            store16(dptr + (size_t)i * p.dst.pitch,
+            put16<CLIP>(dptr + (size_t)i * p.dst.pitch,
                     make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7])), valid);
             h0 = h1; h1 = h2; h2 = h3; h3 = h4;
         }
@@ -528,8 +536,11 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
     const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // tile row of source row yw - r
     uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
 
-    if (nrows == R) compute_band<OP, C, R, true>(colp, dptr, p, R, cx);
-    else compute_band<OP, C, R, false>(colp, dptr, p, nrows, cx);
+    // warp-uniform: does this tile column contain the partial last chunk of an unpadded destination row?
+    const bool clip = p.dst_exact && bx0 + kTileBytes > p.rowbytes && (p.rowbytes & 15) != 0;
+    if (clip) compute_band<OP, C, R, false, true>(colp, dptr, p, nrows, cx);
+    else if (nrows == R) compute_band<OP, C, R, true, false>(colp, dptr, p, R, cx);
+    else compute_band<OP, C, R, false, false>(colp, dptr, p, nrows, cx);
 }
 
 template <int OP, int C, int R, int kWarps>
@@ -624,7 +635,8 @@ __global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_co
     }
     const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // source row yw - 3
     const bool store_lane = lane != 0 && lane != 31 && cx < ((p.rowbytes + 15) & ~15);
-    const int valid = p.dst_exact ? p.rowbytes - cx : 16;
+    const bool clip = p.dst_exact && gx0 + kTileBytes > p.rowbytes && (p.rowbytes & 15) != 0;  // block-uniform
+    const int valid = clip ? p.rowbytes - cx : 16;
     uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
 
     Acc8 h0, h1, h2, h3, h4;  // horizontal Gaussian passes of five consecutive source rows
