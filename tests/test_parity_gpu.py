@@ -556,3 +556,38 @@ def test_golden_pattern_cases(ctx, dip):
         img = g[f"{name}/input"]
         for prefix, mname, args in dip.REFERENCE_OPS:
             assert np.array_equal(run_op(ctx, mname, args, img), g[f"{name}/{prefix}"]), f"{name} {prefix}"
+
+
+def test_pipeline_host_rings_and_point_op_row_ranges(ctx, dip, orc):
+    """dip_pipeline_run with host rings smaller than the stream (frame f reads in[f % ring], result lands in
+    out[f % ring]) and dip_apply_rows for a point operation."""
+    rng = np.random.default_rng(31)
+    chunk, in_ring, out_ring, frames = 2, 4, 2, 10
+    h, w, c = 40, 200, 3
+    host_in = ctx.pinned_empty((in_ring, h, w, c))
+    host_in[...] = rng.integers(0, 256, host_in.shape, dtype=np.uint8)
+    ops = [op for _, p, op in ctx.reference_ops() if p in ("inversion", "erosion-cross", "convolution-gaussian-blur-5x5-separated")]
+    fns = [f for p, f in orc.OPERATIONS if p in ("inversion", "erosion-cross", "convolution-gaussian-blur-5x5-separated")]
+    outs = [ctx.pinned_empty((out_ring, h, w, c)) for _ in ops]
+    pipe = ctx.pipeline(w, h, c, chunk, ops)
+    for _ in range(2):  # the pipeline object is reusable
+        pipe.run(host_in, frames, outs)
+        for o, fn in zip(outs, fns):
+            for slot in range(out_ring):
+                f = frames - out_ring + slot          # the last frames written to each ring slot
+                assert f % out_ring == slot
+                assert np.array_equal(o[slot], fn(host_in[f % in_ring])), (slot, f)
+    pipe.close()
+    for a in [host_in] + outs:
+        dip.ops.free_pinned(a)
+    # a point op over a row range
+    img = rng.integers(0, 256, (50, 77, 4), dtype=np.uint8)
+    src = ctx.from_array(img)
+    dst = ctx.from_array(np.zeros_like(img))
+    inv = [op for _, p, op in ctx.reference_ops() if p == "inversion"][0]
+    ctx.apply_rows(inv, src, 0, 50, 10, 20, dst, 5)
+    got = dst.download()
+    want = np.zeros_like(img)
+    want[5:25] = 255 - img[10:30]
+    assert np.array_equal(got, want)
+    src.close(); dst.close()
