@@ -543,13 +543,24 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
     else compute_band<OP, C, R, false, false>(colp, dptr, p, nrows, cx);
 }
 
+// Development knobs (dip_debug_set): "tile_rows" 0 = automatic, 64 or 32 forces the tile height.
+struct Knobs { int tile_rows = 0, fused_rows = 0, extra_smem = 0; };
+Knobs g_knobs;
+
 template <int OP, int C, int R, int kWarps>
 int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
     constexpr int r = op_radius_y(OP);
     constexpr int kThreads = kWarps * 32;
     constexpr int TH = kWarps * R;
     constexpr int ROWS = TH + 2 * r;
-    constexpr int smem_bytes = ROWS * kRowBytes + 16;
+    // Resident CTAs per SM.  The tile alone allows 6 (which the issue-bound Gaussians want: measured +11 % time at 5);
+    // the HBM-bound ops run faster with fewer tiles in flight (256-frame stack, us per frame: 3x3 erosions 7.30 at 6,
+    // 7.30 at 5, 7.07 at 4, 7.8 at 3; GaussianBlur 7.29 / 7.18 / 7.28), so their launches ask for more dynamic shared
+    // memory than the tile needs.  Only the stack shape (R = 15); profiles/r1_occupancy_sweep.md.
+    constexpr int kCtasPerSm = R != 15 ? 0 : (OP == kErodeSq3 || OP == kErodeCross3 || OP == kDilateSq3 || OP == kDilateCross3) ? 4 : OP == kGauss3 ? 5 : 0;
+    constexpr int kTileSmem = ROWS * kRowBytes + 16;
+    constexpr int kPadded = kCtasPerSm ? (227 * 1024) / kCtasPerSm - 1024 - 512 : 0;  // 1 KiB per CTA is reserved by the driver
+    const int smem_bytes = (kPadded > kTileSmem ? kPadded : kTileSmem) + g_knobs.extra_smem;
     const CUtensorMap* map = nullptr;
     int rc = get_tmap(ctx, const_cast<dip_image*>(src), kBoxWords, ROWS, &map);
     if (rc != DIP_OK) return rc;
@@ -566,7 +577,7 @@ int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGe
     if (p.tiles_y > 65535 || src->v.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
     static std::atomic<uint64_t> attr_set{0};  // per instantiation, one bit per device
     const uint64_t dev_bit = 1ull << (ctx->device & 63);
-    if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
+    if (!(attr_set.load(std::memory_order_relaxed) & dev_bit) || g_knobs.extra_smem) {
         DIP_CUDA(ctx, cudaFuncSetAttribute(stencil_kernel<OP, C, R, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
@@ -721,9 +732,6 @@ int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const 
     return DIP_OK;
 }
 
-// Development knob (dip_debug_set "tile_rows"): 0 = automatic, 64 or 32 forces the tile height.
-struct Knobs { int tile_rows = 0, fused_rows = 0; };
-Knobs g_knobs;
 
 template <int OP>
 int launch_tiled_c(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
@@ -938,6 +946,7 @@ extern "C" {
 
 int dip_debug_set(const char* key, int value) {
     if (!key) return fail(nullptr, DIP_ERR_ARG, "null key");
+    if (!strcmp(key, "extra_smem")) { g_knobs.extra_smem = value; return DIP_OK; }
     if (!strcmp(key, "tile_rows")) g_knobs.tile_rows = value;
     else if (!strcmp(key, "fused_rows")) g_knobs.fused_rows = value;
     else return fail(nullptr, DIP_ERR_ARG, "unknown knob %s", key);

@@ -14,7 +14,7 @@ ctx = dip.Context(0)
 src = ctx.image(3504, 2336, 3, frames=frames).synth_fill(seed=0)
 dst = ctx.image(3504, 2336, 3, frames=frames)
 ops = {p: op for _, p, op in ctx.reference_ops()}
-names = ["inversion", "grayscale", "erosion-cross", "erosion-square", "gaussian-blur-3x3", "convolution-gaussian-blur-3x3",
+names = ["inversion", "grayscale", "erosion-cross", "erosion-square", "erosion-square-separated", "gaussian-blur-3x3", "convolution-gaussian-blur-3x3",
          "convolution-gaussian-blur-3x3-separated", "convolution-gaussian-blur-5x5", "convolution-gaussian-blur-5x5-separated"]
 res = {(v, n): [] for v, _ in variants for n in names}
 for r in range(rounds):
