@@ -117,7 +117,8 @@ static bool read_file(const std::string& path, std::vector<uint8_t>& out) {
 
 // `image.data` empty + jpeg != nullptr: the pixels are decoded from `jpeg_bytes` directly into the device image.
 static void perform_benchmark(dip_ctx* ctx, const Pnm& image, const std::string& filename, const fs::path& outdir, size_t rounds,
-                              bool sync_every_call, int batch, JpegIo* jpeg, const std::vector<uint8_t>& jpeg_bytes) {
+                              bool sync_every_call, int batch, JpegIo* jpeg, const std::vector<uint8_t>& jpeg_bytes,
+                              const std::string& csv_path, const std::string& tool) {
     const int width = image.w, height = image.h, channels = image.c;
     const size_t frame_bytes = (size_t)width * height * channels;
     dip_image *d_input = nullptr, *d_output = nullptr;                              // sycl:260-262 (no d_aux: fused separable ops)
@@ -161,9 +162,11 @@ static void perform_benchmark(dip_ctx* ctx, const Pnm& image, const std::string&
 
     int biggest = 0;
     for (const auto& op : operations) biggest = std::max(biggest, (int)std::get<0>(op).length());
+    std::vector<double> csv_row;
     for (auto& operation : operations) {                                                                  // sycl:365-375
         auto& [description, prefix, func] = operation;
         auto [once, times] = measure_time(func, rounds, sync);
+        csv_row.push_back(times);
         std::printf("| %-*s | %10.6fs (once) | %10.6fs (%zu times) |\n", biggest, description.c_str(), once, times, rounds);
         if (prefix.empty()) continue;
         if (jpeg) {  // encode frame 0 of the result on the GPU; only the bitstream comes back
@@ -187,6 +190,19 @@ static void perform_benchmark(dip_ctx* ctx, const Pnm& image, const std::string&
         if (!write_pnm((outdir / (prefix + "-" + stem + ext)).string(), h_out, width, height, channels))
             std::fprintf(stderr, "Error: could not write output for %s\n", prefix.c_str());
     }
+    if (!csv_path.empty()) {
+        // one row in the layout of the reference's assets/results.csv (read by plot.py:6-18): seconds per round; 9 decimals because a B200 op takes microseconds
+        const bool fresh = !fs::exists(csv_path) || fs::file_size(csv_path) == 0;
+        std::ofstream csv(csv_path, std::ios::app);
+        if (fresh)
+            csv << "Tool,Upload,Download,Copy,Inversion,Grayscale,Threshold,Erosion-3x3-Cross,Erosion-3x3-Square,Erosion-1x3+3x1-Square,"
+                   "Convolution-3x3,Convolution-1x3+3x1,Convolution-5x5,Convolution-1x5+5x1,Gaussian-Blur-3x3\n";
+        csv << tool;
+        char buf[32];
+        for (double v : csv_row) { std::snprintf(buf, sizeof buf, ",%.9f", v); csv << buf; }
+        csv << "\n";
+        if (!csv) std::fprintf(stderr, "Error: could not append to '%s'\n", csv_path.c_str());
+    }
     dip_host_free(h_in); dip_host_free(h_out);
     dip_image_destroy(d_input); dip_image_destroy(d_output);                                              // sycl:377-386
 }
@@ -196,16 +212,19 @@ int main(int argc, char** argv) {
     size_t rounds = default_rounds;
     bool sync_every_call = true;
     int device = 0, batch = 1;
+    std::string csv_path, tool = "B200";
     std::vector<std::string> pos;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "--no-sync") sync_every_call = false;
         else if (a == "--device" && i + 1 < argc) device = std::atoi(argv[++i]);
         else if (a == "--batch" && i + 1 < argc) batch = std::max(1, std::atoi(argv[++i]));
+        else if (a == "--csv" && i + 1 < argc) csv_path = argv[++i];
+        else if (a == "--tool" && i + 1 < argc) tool = argv[++i];
         else pos.push_back(a);
     }
     if (pos.size() < 2 || pos.size() > 3) {                                                               // sycl:393-396
-        std::fprintf(stderr, "Usage: %s [INPUT IMAGE] [OUTPUT PATH] [[ROUNDS] = %zu] [--no-sync] [--device N] [--batch N]\n",
+        std::fprintf(stderr, "Usage: %s [INPUT IMAGE] [OUTPUT PATH] [[ROUNDS] = %zu] [--no-sync] [--device N] [--batch N] [--csv FILE [--tool NAME]]\n",
                      fs::path(argv[0]).filename().string().c_str(), rounds);
         return 1;
     }
@@ -249,7 +268,7 @@ int main(int argc, char** argv) {
         return 6;
     }
     if (!fs::exists(outpath)) fs::create_directories(outpath);                                            // sycl:452-454
-    perform_benchmark(ctx, image, inpath.filename().string(), outpath, rounds, sync_every_call, batch, jpeg, jpeg_bytes);  // sycl:460
+    perform_benchmark(ctx, image, inpath.filename().string(), outpath, rounds, sync_every_call, batch, jpeg, jpeg_bytes, csv_path, tool);  // sycl:460
     jpeg_io_destroy(jpeg);
     dip_shutdown(ctx);
     return 0;

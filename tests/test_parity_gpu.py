@@ -345,10 +345,17 @@ def test_native_cli_driver_matches_oracle(ctx, dip, orc, tmp_path):
     out = tmp_path / "out"
     assert subprocess.run([exe], capture_output=True).returncode == 1                      # usage
     assert subprocess.run([exe, str(tmp_path / "missing.ppm"), str(out)], capture_output=True).returncode == 6
-    r = subprocess.run([exe, str(src), str(out) + "/", "3"], capture_output=True, text=True)
+    csv = tmp_path / "results.csv"
+    r = subprocess.run([exe, str(src), str(out) + "/", "3", "--csv", str(csv)], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     rows = [l for l in r.stdout.splitlines() if l.startswith("|")]
     assert len(rows) == 14 and "(3 times)" in rows[0] and rows[0].startswith("| Upload")
+    # --csv: one row in the layout of the reference's assets/results.csv (the input of plot.py:6-18)
+    head, row = csv.read_text().splitlines()
+    assert head.split(",") == ["Tool", "Upload", "Download", "Copy", "Inversion", "Grayscale", "Threshold", "Erosion-3x3-Cross",
+                               "Erosion-3x3-Square", "Erosion-1x3+3x1-Square", "Convolution-3x3", "Convolution-1x3+3x1",
+                               "Convolution-5x5", "Convolution-1x5+5x1", "Gaussian-Blur-3x3"]
+    assert row.split(",")[0] == "B200" and len(row.split(",")) == 15 and all(float(v) > 0 for v in row.split(",")[1:])
     for prefix, ofn in orc.OPERATIONS:
         data = open(out / f"{prefix}-in.ppm", "rb").read()
         hdr = b"P6\n211 97\n255\n"
