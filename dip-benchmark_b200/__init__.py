@@ -12,9 +12,9 @@ The directory is named ``dip-benchmark_b200`` (not an identifier); load it with
 ``from _dip_pkg import load; dip = load()`` from the repository root.
 """
 from .capi import DipError, lib, lib_path, build_library, declared_symbols  # noqa: F401
-from .ops import Context, Image, REFERENCE_OPS  # noqa: F401
+from .ops import Context, Image, REFERENCE_OPS, make_op  # noqa: F401
 from . import shard  # noqa: F401
 from . import mosaic  # noqa: F401
 
-__all__ = ["Context", "Image", "DipError", "REFERENCE_OPS", "lib", "lib_path", "build_library",
+__all__ = ["Context", "Image", "DipError", "REFERENCE_OPS", "make_op", "lib", "lib_path", "build_library",
            "declared_symbols", "shard", "mosaic"]

@@ -74,6 +74,7 @@ struct dip_ctx {
     uint64_t* d_checksums = nullptr;
     int d_checksums_cap = 0;
     std::vector<cudaEvent_t> marks;
+    dip_image* chain_scratch = nullptr;  // intermediate stack of dip_apply_chain (library-owned, reallocated on shape change)
     std::string last_error;
 };
 
@@ -121,6 +122,44 @@ cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// ---- per-byte maps (dip_apply_chain) ---------------------------------------------------
+// The byte-wise point ops (copy, inversion, threshold) are closed under composition: any sequence of them is
+// x, 255 - x, or a step  x > t ? hi : lo.  A chain therefore carries ONE map where the reference would run
+// one kernel per op; kernels evaluate it branch-free on four bytes at a time as
+//     (x & keep) ^ (lo4 ^ (gt(x, t4) & flip4))          keep = ~0 for x / 255 - x, 0 for a step.
+struct ByteMap {
+    int kind = 0;            // 0: x   1: 255 - x   2: x > t ? hi : lo
+    uint8_t t = 0, hi = 0, lo = 0;
+    bool identity() const { return kind == 0; }
+    uint8_t eval(uint8_t x) const { return kind == 0 ? x : kind == 1 ? (uint8_t)(255 - x) : (x > t ? hi : lo); }
+    static ByteMap invert() { ByteMap m; m.kind = 1; return m; }
+    static ByteMap step(uint8_t t, uint8_t hi, uint8_t lo) { ByteMap m; m.kind = 2; m.t = t; m.hi = hi; m.lo = lo; return m; }
+    // the map "first *this, then g"
+    ByteMap then(const ByteMap& g) const {
+        if (kind == 2) return step(t, g.eval(hi), g.eval(lo));
+        if (kind == 0) return g;
+        // *this is 255 - x
+        if (g.kind == 0) return *this;
+        if (g.kind == 1) return ByteMap{};
+        // g(255 - x) = (255 - x > g.t) ? g.hi : g.lo = (x > 254 - g.t) ? g.lo : g.hi
+        if (g.t == 255) return step(255, g.lo, g.lo);  // g is the constant lo
+        return step((uint8_t)(254 - g.t), g.lo, g.hi);
+    }
+};
+struct MapParams {
+    uint32_t t4 = 0, keep = 0xFFFFFFFFu, flip4 = 0, lo4 = 0;  // identity
+};
+inline MapParams map_params(const ByteMap& m) {
+    MapParams p;
+    if (m.kind == 1) { p.lo4 = 0xFFFFFFFFu; }
+    else if (m.kind == 2) { p.t4 = m.t * 0x01010101u; p.keep = 0; p.flip4 = (uint32_t)(m.hi ^ m.lo) * 0x01010101u; p.lo4 = m.lo * 0x01010101u; }
+    return p;
+}
+// Maps fused into a tiled stencil launch: `pre` rewrites the source tile in shared memory, `post` the result words.
+struct ChainMaps {
+    ByteMap pre, post;
+};
+
 #ifdef __CUDACC__
 // 16-byte result store.  Library-owned images pad every row to 16 bytes, so the last vector of a row may spill
 // into the padding; a wrapped region of interest has real pixels there, so only `valid` bytes are written.
@@ -134,6 +173,27 @@ __device__ __forceinline__ void store16(uint8_t* p, const uint4& v, int valid) {
 }
 // bytes of the 16-byte chunk starting at byte `cx` of a row that may be written
 __device__ __forceinline__ int chunk_valid(int cx, int rowbytes, bool exact) { return exact ? rowbytes - cx : 16; }
+
+__device__ __forceinline__ uint32_t map_word(uint32_t x, const MapParams& m) {  // branch-free form
+    return (x & m.keep) ^ (m.lo4 ^ (__vcmpgtu4(x, m.t4) & m.flip4));
+}
+__device__ __forceinline__ uint32_t map_step(uint32_t x, const MapParams& m) { return m.lo4 ^ (__vcmpgtu4(x, m.t4) & m.flip4); }
+// N words through one map; the kind test is uniform over the launch, so x / 255 - x cost one LOP3 per word
+template <int N>
+__device__ __forceinline__ void map_words(uint32_t (&w)[N], const MapParams& m) {
+    if (m.keep) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) w[i] ^= m.lo4;
+    } else {
+#pragma unroll
+        for (int i = 0; i < N; ++i) w[i] = map_step(w[i], m);
+    }
+}
+__device__ __forceinline__ uint4 map_vec(uint4 v, const MapParams& m) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    map_words(w, m);
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
@@ -153,6 +213,8 @@ enum PointOp { kCopy = 0, kInvert = 1, kThreshold = 2 };
 int launch_point(dip_ctx* ctx, PointOp op, const ImgView& src, const ImgView& dst, uint8_t thresh,
                  uint8_t maxval);
 int launch_grayscale(dip_ctx* ctx, const ImgView& src, const ImgView& dst);
+// dst = post(gray?(pre(src))) in one pass (dip_apply_chain's point segment)
+int launch_point_chain(dip_ctx* ctx, const ImgView& src, const ImgView& dst, const ByteMap& pre, bool gray, const ByteMap& post);
 int launch_synth(dip_ctx* ctx, const ImgView& dst, uint32_t seed, uint64_t first_row);
 int launch_checksum(dip_ctx* ctx, const ImgView& src, uint64_t first_row, uint64_t* d_out);
 int launch_fill(dip_ctx* ctx, uint8_t* p, size_t bytes, uint32_t value);
@@ -165,13 +227,20 @@ struct RowGeom {
     int valid_y0, valid_y1, out_y0, out_y1, dst_y0;
 };
 enum class Morph { Erode, Dilate };
+// `maps` (optional): per-byte maps fused into the launch; only the tiled kernels take them (stencil_tiled_op >= 0)
 int stencil_morph(dip_ctx* ctx, Morph m, const dip_image* src, dip_image* dst, const uint8_t* mask,
-                  int mw, int mh, const RowGeom& g);
+                  int mw, int mh, const RowGeom& g, const ChainMaps* maps = nullptr);
 int stencil_convolve(dip_ctx* ctx, const dip_image* src, dip_image* dst, const float* k, int kw,
-                     int kh, const RowGeom& g);
+                     int kh, const RowGeom& g, const ChainMaps* maps = nullptr);
 int stencil_convolve_sep(dip_ctx* ctx, const dip_image* src, dip_image* dst, const float* krow,
-                         int kw, const float* kcol, int kh, const RowGeom& g);
-int stencil_gaussian3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g);
+                         int kw, const float* kcol, int kh, const RowGeom& g, const ChainMaps* maps = nullptr);
+int stencil_gaussian3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps = nullptr);
+// The tiled kernel (stencil_tiled.cuh: StencilOp) that computes `op`, or -1 (direct kernel, point op, fused chain).
+int stencil_tiled_op(const dip_op& op);
+bool stencil_is_gauss5(const dip_op& op);     // filter2D with the 5x5 Gaussian
+bool stencil_is_erode_sq3(const dip_op& op);  // 3x3 all-ones erosion (either form)
+// stencil_mapped.cu: tiled kernel `op` with the maps fused in
+int launch_tiled_mapped(dip_ctx* ctx, int op, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps& maps);
 int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g);
 
 // TMA descriptor of an image view seen as a (pitch/4 words, rows, frames) u32 tensor.

@@ -110,6 +110,167 @@ int dip_apply(dip_ctx* ctx, const dip_op* op, const dip_image* src, dip_image* d
     return fail(ctx, DIP_ERR_ARG, "unknown operation kind %d", op->kind);
 }
 
+// ---- op chains ----------------------------------------------------------------------------------
+}  // extern "C"
+
+namespace {
+
+// One pass over HBM of a planned chain.
+struct ChainPass {
+    enum Kind { Point, Stencil, GaussErode } kind = Point;
+    // Point: dst = post(gray?(pre(src)));  Stencil: ops[op_index] with pre / post fused (tiled kernels only)
+    ByteMap pre, post;
+    bool gray = false;
+    int op_index = -1;
+    bool tiled = false;
+};
+
+bool is_byte_op(int kind) { return kind == DIP_OP_COPY || kind == DIP_OP_INVERT || kind == DIP_OP_THRESHOLD; }
+bool is_stencil_op(int kind) {
+    return kind == DIP_OP_ERODE || kind == DIP_OP_DILATE || kind == DIP_OP_ERODE_SEPARABLE || kind == DIP_OP_CONVOLVE ||
+           kind == DIP_OP_CONVOLVE_SEPARABLE || kind == DIP_OP_GAUSSIAN_BLUR3X3 || kind == DIP_OP_GAUSS5X5_ERODE3X3;
+}
+
+// Greedy plan.  A pending point segment is (A, gray?, B): bytes through A, then grayscale, then bytes through B.
+int plan_chain(dip_ctx* ctx, const dip_op* ops, int n, int channels, std::vector<ChainPass>& plan) {
+    ByteMap a, b;
+    bool gray = false, pending = false;
+    auto flush_point = [&] {  // the pending segment becomes a pass of its own, or the epilogue of the previous tiled stencil
+        if (!pending) return;
+        if (!gray && !plan.empty() && plan.back().kind == ChainPass::Stencil && plan.back().tiled) {
+            plan.back().post = plan.back().post.then(a);
+        } else if (gray || !a.identity()) {
+            ChainPass p;
+            p.pre = a; p.gray = gray; p.post = b;
+            plan.push_back(p);
+        }
+        a = ByteMap{}; b = ByteMap{}; gray = false; pending = false;
+    };
+    for (int i = 0; i < n; ++i) {
+        const dip_op& op = ops[i];
+        if (is_byte_op(op.kind)) {
+            const ByteMap m = op.kind == DIP_OP_INVERT ? ByteMap::invert() : op.kind == DIP_OP_THRESHOLD ? ByteMap::step(op.thresh, op.maxval, 0) : ByteMap{};
+            if (gray) b = b.then(m); else a = a.then(m);
+            pending = true;
+        } else if (op.kind == DIP_OP_GRAYSCALE) {
+            if (channels == 1) { pending = true; continue; }  // GRAY2GRAY: identity
+            if (gray) {
+                // gray(B(Y,Y,Y)) = B(Y) on the colour channels (the weights sum to 2^15), so a second grayscale changes
+                // nothing on 3 channels; with alpha it resets alpha to 255, which (A, gray, B) cannot express: new pass
+                if (channels == 3) continue;
+                ChainPass p;
+                p.pre = a; p.gray = true; p.post = b;
+                plan.push_back(p);
+                a = ByteMap{}; b = ByteMap{};
+            }
+            gray = true; pending = true;
+        } else if (is_stencil_op(op.kind)) {
+            ChainPass p;
+            p.kind = ChainPass::Stencil;
+            p.op_index = i;
+            p.tiled = stencil_tiled_op(op) >= 0;
+            if (op.kind == DIP_OP_GAUSS5X5_ERODE3X3) p.kind = ChainPass::GaussErode;
+            // 5x5 Gaussian directly followed by the 3x3 square erosion: the fused kernel
+            const bool pair = stencil_is_gauss5(op) && i + 1 < n && stencil_is_erode_sq3(ops[i + 1]);
+            if (pair) p.kind = ChainPass::GaussErode;
+            if (p.kind == ChainPass::GaussErode) p.tiled = false;  // the fused kernel takes no maps
+            if (pending) {
+                const bool prev_takes_it = !gray && !plan.empty() && plan.back().kind == ChainPass::Stencil && plan.back().tiled;
+                if (prev_takes_it || !p.tiled) {
+                    flush_point();
+                } else if (gray) {  // (A, gray) is a pass; B rides in front of the stencil
+                    ChainPass g;
+                    g.pre = a; g.gray = true;
+                    plan.push_back(g);
+                    p.pre = b;
+                } else {
+                    p.pre = a;
+                }
+                a = ByteMap{}; b = ByteMap{}; gray = false; pending = false;
+            }
+            plan.push_back(p);
+            if (pair) ++i;
+        } else {
+            return fail(ctx, DIP_ERR_ARG, "unknown operation kind %d at chain position %d", op.kind, i);
+        }
+    }
+    flush_point();
+    if (plan.empty()) plan.push_back(ChainPass{});  // nothing but identities: one copy
+    return DIP_OK;
+}
+
+int ensure_scratch(dip_ctx* ctx, const dip_image* like) {
+    dip_image* s = ctx->chain_scratch;
+    if (s && s->v.width == like->v.width && s->v.height == like->v.height && s->v.channels == like->v.channels && s->v.frames == like->v.frames)
+        return DIP_OK;
+    if (s) {
+        DIP_CUDA(ctx, cudaStreamSynchronize(ctx->compute));  // kernels may still be reading the old one
+        dip_image_destroy(s);
+        ctx->chain_scratch = nullptr;
+    }
+    return dip_image_create_batch(ctx, like->v.width, like->v.height, like->v.channels, like->v.frames, &ctx->chain_scratch);
+}
+
+int run_stencil_pass(dip_ctx* ctx, const dip_op& op, const ChainPass& ps, const dip_image* src, dip_image* dst) {
+    const RowGeom g = full_geom(src);
+    ChainMaps maps;
+    maps.pre = ps.pre; maps.post = ps.post;
+    const ChainMaps* mp = (ps.pre.identity() && ps.post.identity()) ? nullptr : &maps;
+    if (ps.kind == ChainPass::GaussErode) return stencil_gauss5_erode3(ctx, src, dst, g);
+    switch (op.kind) {
+        case DIP_OP_ERODE: return stencil_morph(ctx, Morph::Erode, src, dst, op.mask, op.mask_w, op.mask_h, g, mp);
+        case DIP_OP_DILATE: return stencil_morph(ctx, Morph::Dilate, src, dst, op.mask, op.mask_w, op.mask_h, g, mp);
+        case DIP_OP_ERODE_SEPARABLE: {
+            if (op.mask_w < 1 || op.mask_h < 1 || op.mask_w * op.mask_h > 225) return fail(ctx, DIP_ERR_ARG, "bad separable mask %dx%d", op.mask_w, op.mask_h);
+            std::vector<uint8_t> ones((size_t)op.mask_w * op.mask_h, 1);
+            return stencil_morph(ctx, Morph::Erode, src, dst, ones.data(), op.mask_w, op.mask_h, g, mp);
+        }
+        case DIP_OP_CONVOLVE: return stencil_convolve(ctx, src, dst, op.kernel, op.kw, op.kh, g, mp);
+        case DIP_OP_CONVOLVE_SEPARABLE: return stencil_convolve_sep(ctx, src, dst, op.kernel, op.kw, op.kernel_col, op.kh, g, mp);
+        case DIP_OP_GAUSSIAN_BLUR3X3: return stencil_gaussian3(ctx, src, dst, g, mp);
+    }
+    return fail(ctx, DIP_ERR_ARG, "not a stencil operation: %d", op.kind);
+}
+
+}  // namespace
+
+extern "C" {
+
+int dip_chain_passes(const dip_op* ops, int n, int channels, int* passes) {
+    if (!ops || n < 1 || !passes || (channels != 1 && channels != 3 && channels != 4)) return fail(nullptr, DIP_ERR_ARG, "bad argument");
+    std::vector<ChainPass> plan;
+    const int rc = plan_chain(nullptr, ops, n, channels, plan);
+    if (rc != DIP_OK) return rc;
+    *passes = (int)plan.size();
+    return DIP_OK;
+}
+
+int dip_apply_chain(dip_ctx* ctx, const dip_op* ops, int n, const dip_image* src, dip_image* dst) {
+    if (!ctx || !ops || n < 1) return fail(ctx, DIP_ERR_ARG, "bad argument");
+    int rc = check_pair(ctx, src, dst, true);
+    if (rc != DIP_OK) return rc;
+    std::vector<ChainPass> plan;
+    if ((rc = plan_chain(ctx, ops, n, src->v.channels, plan)) != DIP_OK) return rc;
+    const int k = (int)plan.size();
+    bool any_stencil = false;
+    for (const ChainPass& p : plan) any_stencil |= p.kind != ChainPass::Point;
+    if (any_stencil && (rc = check_pair(ctx, src, dst, false)) != DIP_OK) return rc;
+    if (k > 1 && (rc = ensure_scratch(ctx, src)) != DIP_OK) return rc;
+    if ((rc = begin_op(ctx, src, dst)) != DIP_OK) return rc;
+    // pass j (1-based) writes dst when k - j is even, the scratch stack otherwise: the last pass lands in dst and no
+    // pass reads what it writes
+    const dip_image* in = src;
+    for (int j = 1; j <= k; ++j) {
+        const ChainPass& p = plan[j - 1];
+        dip_image* out = ((k - j) & 1) ? ctx->chain_scratch : dst;
+        if (p.kind == ChainPass::Point) rc = launch_point_chain(ctx, in->v, out->v, p.pre, p.gray, p.post);
+        else rc = run_stencil_pass(ctx, ops[p.op_index], p, in, out);
+        if (rc != DIP_OK) return rc;
+        in = out;
+    }
+    return DIP_OK;
+}
+
 // One-shot form of the pipeline below.
 int dip_run_ops_host(dip_ctx* ctx, const uint8_t* host_in, int w, int h, int c, int frames, const dip_op* ops, int n_ops,
                      uint8_t* const* host_out, int chunk_frames) {

@@ -38,22 +38,29 @@ __device__ __forceinline__ uint32_t luma(uint32_t px, uint32_t wlo, uint32_t whi
     return (hi * 256u + lo) >> 15;
 }
 
+constexpr int kGray4 = 3;       // BGRA -> Y,Y,Y,255
+constexpr int kMap = 4;         // any composition of the byte-wise ops (dip_internal.h: ByteMap)
+constexpr int kMapGray4 = 5;    // post(gray(pre(x))) on BGRA
+
+// `m`: the threshold (t4, flip4 = maxval) or the map; `post`: second map of kMapGray4
 template <int OP>
-__device__ __forceinline__ uint32_t point_word(uint32_t x, uint32_t t4, uint32_t m4) {
+__device__ __forceinline__ uint32_t point_word(uint32_t x, const MapParams& m, const MapParams& post) {
     if (OP == kCopy) return x;
     if (OP == kInvert) return ~x;
-    if (OP == kThreshold) return __vcmpgtu4(x, t4) & m4;
-    // OP == 3: BGRA -> Y,Y,Y,255
+    if (OP == kThreshold) return __vcmpgtu4(x, m.t4) & m.flip4;
+    if (OP == kMap) return map_word(x, m);
+    if (OP == kMapGray4) x = map_word(x, m);
     const uint32_t y = luma(x, kWLo0, kWHi0);
-    return y * 0x00010101u | 0xFF000000u;
+    const uint32_t g = y * 0x00010101u | 0xFF000000u;
+    return OP == kMapGray4 ? map_word(g, post) : g;
 }
 
 template <int OP>
-__device__ __forceinline__ uint4 point_vec(uint4 v, uint32_t t4, uint32_t m4) {
-    v.x = point_word<OP>(v.x, t4, m4);
-    v.y = point_word<OP>(v.y, t4, m4);
-    v.z = point_word<OP>(v.z, t4, m4);
-    v.w = point_word<OP>(v.w, t4, m4);
+__device__ __forceinline__ uint4 point_vec(uint4 v, const MapParams& m, const MapParams& post) {
+    v.x = point_word<OP>(v.x, m, post);
+    v.y = point_word<OP>(v.y, m, post);
+    v.z = point_word<OP>(v.z, m, post);
+    v.w = point_word<OP>(v.w, m, post);
     return v;
 }
 
@@ -63,7 +70,7 @@ __device__ __forceinline__ uint4 point_vec(uint4 v, uint32_t t4, uint32_t m4) {
 template <int OP, int UNROLL>
 __global__ void __launch_bounds__(kThreads) point_flat_kernel(const uint4* __restrict__ src,
                                                               uint4* __restrict__ dst, size_t nvec,
-                                                              uint32_t t4, uint32_t m4) {
+                                                              const MapParams m, const MapParams post) {
     pdl_launch_dependents();
     pdl_wait();
     const size_t base = (size_t)blockIdx.x * (kThreads * UNROLL) + threadIdx.x;
@@ -72,12 +79,12 @@ __global__ void __launch_bounds__(kThreads) point_flat_kernel(const uint4* __res
 #pragma unroll
         for (int j = 0; j < UNROLL; ++j) v[j] = ld_stream(src + base + (size_t)j * kThreads);
 #pragma unroll
-        for (int j = 0; j < UNROLL; ++j) st_stream(dst + base + (size_t)j * kThreads, point_vec<OP>(v[j], t4, m4));
+        for (int j = 0; j < UNROLL; ++j) st_stream(dst + base + (size_t)j * kThreads, point_vec<OP>(v[j], m, post));
     } else {
 #pragma unroll
         for (int j = 0; j < UNROLL; ++j) {
             const size_t i = base + (size_t)j * kThreads;
-            if (i < nvec) st_stream(dst + i, point_vec<OP>(ld_stream(src + i), t4, m4));
+            if (i < nvec) st_stream(dst + i, point_vec<OP>(ld_stream(src + i), m, post));
         }
     }
 }
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(kThreads) point_flat_kernel(const uint4* __res
 // Strided layouts (wrapped memory whose pitches differ): one vector per thread.
 template <int OP>
 __global__ void __launch_bounds__(kThreads) point_rows_kernel(ImgView src, ImgView dst, int vec_per_row,
-                                                              size_t total, uint32_t t4, uint32_t m4) {
+                                                              size_t total, const MapParams m, const MapParams post) {
     pdl_launch_dependents();
     pdl_wait();
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
@@ -106,12 +113,31 @@ __global__ void __launch_bounds__(kThreads) point_rows_kernel(ImgView src, ImgVi
         for (int i = 0; i < valid; ++i) w[i >> 2] |= (uint32_t)s[i] << (8 * (i & 3));
         v = make_uint4(w[0], w[1], w[2], w[3]);
     }
-    store16(d, point_vec<OP>(v, t4, m4), valid);
+    store16(d, point_vec<OP>(v, m, post), valid);
 }
 
 // BGR grayscale: a thread converts one 48-byte group = 16 pixels = 3 vectors.
-template <bool exact>  // exact: rows are not padded to 16 bytes (wrapped regions of interest)
-__global__ void __launch_bounds__(kThreads) gray3_kernel(ImgView src, ImgView dst, int groups_per_row, size_t total) {
+// 4 BGR pixels in 3 words -> 4 x (Y,Y,Y); MAPPED: post(gray(pre(x)))
+template <bool MAPPED>
+__device__ __forceinline__ void gray3_words(const uint32_t* w, uint32_t* o, const MapParams& pre, const MapParams& post) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {  // 4 pixels per 3 words
+        uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
+        if (MAPPED) { a = map_word(a, pre); b = map_word(b, pre); c = map_word(c, pre); }
+        const uint32_t y0 = luma(a, kWLo0, kWHi0);                          // bytes 0,1,2 of a
+        const uint32_t y1 = luma(__byte_perm(a, b, 0x7543), kWLo0, kWHi0);  // a.3, b.0, b.1
+        const uint32_t y2 = luma(__byte_perm(b, c, 0x7432), kWLo0, kWHi0);  // b.2, b.3, c.0
+        const uint32_t y3 = luma(c, kWLo1, kWHi1);                          // bytes 1,2,3 of c
+        o[3 * q + 0] = y0 * 0x00010101u | (y1 << 24);
+        o[3 * q + 1] = y1 * 0x00000101u | (y2 * 0x01010000u);
+        o[3 * q + 2] = y2 | (y3 * 0x01010100u);
+        if (MAPPED) { o[3 * q] = map_word(o[3 * q], post); o[3 * q + 1] = map_word(o[3 * q + 1], post); o[3 * q + 2] = map_word(o[3 * q + 2], post); }
+    }
+}
+
+template <bool exact, bool MAPPED>  // exact: rows are not padded to 16 bytes (wrapped regions of interest)
+__global__ void __launch_bounds__(kThreads) gray3_kernel(ImgView src, ImgView dst, int groups_per_row, size_t total,
+                                                         const MapParams pre, const MapParams post) {
     pdl_launch_dependents();
     pdl_wait();
     const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
@@ -143,17 +169,7 @@ __global__ void __launch_bounds__(kThreads) gray3_kernel(ImgView src, ImgView ds
         w[4 * j + 0] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
     }
     uint32_t o[12];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {  // 4 pixels per 3 words
-        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
-        const uint32_t y0 = luma(a, kWLo0, kWHi0);                          // bytes 0,1,2 of a
-        const uint32_t y1 = luma(__byte_perm(a, b, 0x7543), kWLo0, kWHi0);  // a.3, b.0, b.1
-        const uint32_t y2 = luma(__byte_perm(b, c, 0x7432), kWLo0, kWHi0);  // b.2, b.3, c.0
-        const uint32_t y3 = luma(c, kWLo1, kWHi1);                          // bytes 1,2,3 of c
-        o[3 * q + 0] = y0 * 0x00010101u | (y1 << 24);
-        o[3 * q + 1] = y1 * 0x00000101u | (y2 * 0x01010000u);
-        o[3 * q + 2] = y2 | (y3 * 0x01010100u);
-    }
+    gray3_words<MAPPED>(w, o, pre, post);
 #pragma unroll
     for (int j = 0; j < 3; ++j)
         if (j < nv) store16(drow + off + 16 * j, make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]), chunk_valid(off + 16 * j, src.rowbytes, exact));
@@ -164,7 +180,9 @@ __global__ void __launch_bounds__(kThreads) gray3_kernel(ImgView src, ImgView ds
 // coalesced 16-byte vectors (the direct kernel above reads 48-byte-strided vectors, 3x the L1 wavefronts, which
 // shows once the SM clock drops under the power cap); each thread still converts its own 48-byte group, read from
 // shared memory at a 48-byte stride (12 banks apart: conflict-free for 128-bit accesses).
-__global__ void __launch_bounds__(kThreads) gray3_flat_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t nvec) {
+template <bool MAPPED>
+__global__ void __launch_bounds__(kThreads) gray3_flat_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t nvec,
+                                                              const MapParams pre, const MapParams post) {
     __shared__ uint4 stage[kThreads * 3];
     pdl_launch_dependents();
     pdl_wait();
@@ -182,17 +200,7 @@ __global__ void __launch_bounds__(kThreads) gray3_flat_kernel(const uint4* __res
         w[4 * j + 0] = v.x; w[4 * j + 1] = v.y; w[4 * j + 2] = v.z; w[4 * j + 3] = v.w;
     }
     uint32_t o[12];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint32_t a = w[3 * q], b = w[3 * q + 1], c = w[3 * q + 2];
-        const uint32_t y0 = luma(a, kWLo0, kWHi0);
-        const uint32_t y1 = luma(__byte_perm(a, b, 0x7543), kWLo0, kWHi0);
-        const uint32_t y2 = luma(__byte_perm(b, c, 0x7432), kWLo0, kWHi0);
-        const uint32_t y3 = luma(c, kWLo1, kWHi1);
-        o[3 * q + 0] = y0 * 0x00010101u | (y1 << 24);
-        o[3 * q + 1] = y1 * 0x00000101u | (y2 * 0x01010000u);
-        o[3 * q + 2] = y2 | (y3 * 0x01010100u);
-    }
+    gray3_words<MAPPED>(w, o, pre, post);
 #pragma unroll
     for (int j = 0; j < 3; ++j) stage[threadIdx.x * 3 + j] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
     __syncthreads();
@@ -275,34 +283,23 @@ bool dense_pair(const ImgView& a, const ImgView& b) {
     return dense(a) && dense(b);
 }
 
-bool use_direct_gray() {  // development switch: DIP_GRAY_DIRECT=1 keeps the strided-load kernel for A/B runs
-    static const bool v = [] { const char* e = getenv("DIP_GRAY_DIRECT"); return e && e[0] == '1'; }();
-    return v;
-}
-
 template <int OP>
-int launch_point_t(dip_ctx* ctx, const ImgView& src, const ImgView& dst, uint32_t t4, uint32_t m4) {
+int launch_point_t(dip_ctx* ctx, const ImgView& src, const ImgView& dst, const MapParams& m, const MapParams& post = MapParams{}) {
     if (dense_pair(src, dst)) {
         const size_t nvec = src.pitch * (size_t)src.height * (size_t)src.frames / 16;
-        // 2 x 16 B per thread measured best on B200 for one image (8.8 us) and for stacks (6.98 TB/s);
-        // DIP_PT_UNROLL=1|4|8 selects the other instantiations (development only).
-        static const int tune_unroll = [] { const char* e = getenv("DIP_PT_UNROLL"); return e ? atoi(e) : 0; }();
-        const int unroll = tune_unroll ? tune_unroll : 2;
+        // 2 x 16 B per thread measured best on B200 for one image (8.8 us) and for stacks (6.98 TB/s); 1, 4 and 8 were slower
+        constexpr int unroll = 2;
         const size_t chunk = (size_t)kThreads * unroll;
         const size_t blocks = (nvec + chunk - 1) / chunk;
         if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-        const uint4* sp = reinterpret_cast<const uint4*>(src.base);
-        uint4* dp = reinterpret_cast<uint4*>(dst.base);
-        if (unroll == 2) DIP_CUDA(ctx, launch_kernel(point_flat_kernel<OP, 2>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, sp, dp, nvec, t4, m4));
-        else if (unroll == 8) DIP_CUDA(ctx, launch_kernel(point_flat_kernel<OP, 8>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, sp, dp, nvec, t4, m4));
-        else if (unroll == 1) DIP_CUDA(ctx, launch_kernel(point_flat_kernel<OP, 1>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, sp, dp, nvec, t4, m4));
-        else DIP_CUDA(ctx, launch_kernel(point_flat_kernel<OP, 4>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, sp, dp, nvec, t4, m4));
+        DIP_CUDA(ctx, launch_kernel(point_flat_kernel<OP, unroll>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute,
+                                    reinterpret_cast<const uint4*>(src.base), reinterpret_cast<uint4*>(dst.base), nvec, m, post));
     } else {
         const int vpr = (src.rowbytes + 15) / 16;
         const size_t total = (size_t)vpr * (size_t)src.height * (size_t)src.frames;
         const size_t blocks = (total + kThreads - 1) / kThreads;
         if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-        DIP_CUDA(ctx, launch_kernel(point_rows_kernel<OP>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, vpr, total, t4, m4));
+        DIP_CUDA(ctx, launch_kernel(point_rows_kernel<OP>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, vpr, total, m, post));
     }
     DIP_CHECK_LAUNCH(ctx, "point kernel");
     return DIP_OK;
@@ -311,24 +308,24 @@ int launch_point_t(dip_ctx* ctx, const ImgView& src, const ImgView& dst, uint32_
 }  // namespace
 
 int launch_point(dip_ctx* ctx, PointOp op, const ImgView& src, const ImgView& dst, uint8_t thresh, uint8_t maxval) {
-    const uint32_t t4 = thresh * 0x01010101u, m4 = maxval * 0x01010101u;
     switch (op) {
-        case kCopy: return launch_point_t<kCopy>(ctx, src, dst, t4, m4);
-        case kInvert: return launch_point_t<kInvert>(ctx, src, dst, t4, m4);
-        case kThreshold: return launch_point_t<kThreshold>(ctx, src, dst, t4, m4);
+        case kCopy: return launch_point_t<kCopy>(ctx, src, dst, MapParams{});
+        case kInvert: return launch_point_t<kInvert>(ctx, src, dst, MapParams{});
+        case kThreshold: return launch_point_t<kThreshold>(ctx, src, dst, map_params(ByteMap::step(thresh, maxval, 0)));
     }
     return fail(ctx, DIP_ERR_ARG, "bad point op");
 }
 
-int launch_grayscale(dip_ctx* ctx, const ImgView& src, const ImgView& dst) {
-    if (src.channels == 1) return launch_point_t<kCopy>(ctx, src, dst, 0, 0);
-    if (src.channels == 4) return launch_point_t<3>(ctx, src, dst, 0, 0);
-    if (dense_pair(src, dst) && src.rowbytes % 48 == 0 && !use_direct_gray()) {
+namespace {
+
+template <bool MAPPED>
+int launch_gray3(dip_ctx* ctx, const ImgView& src, const ImgView& dst, const MapParams& pre, const MapParams& post) {
+    if (dense_pair(src, dst) && src.rowbytes % 48 == 0) {
         const size_t nvec = src.pitch * (size_t)src.height * (size_t)src.frames / 16;
         const size_t blocks = (nvec + kThreads * 3 - 1) / (kThreads * 3);
         if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-        DIP_CUDA(ctx, launch_kernel(gray3_flat_kernel, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute,
-                                    reinterpret_cast<const uint4*>(src.base), reinterpret_cast<uint4*>(dst.base), nvec));
+        DIP_CUDA(ctx, launch_kernel(gray3_flat_kernel<MAPPED>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute,
+                                    reinterpret_cast<const uint4*>(src.base), reinterpret_cast<uint4*>(dst.base), nvec, pre, post));
         DIP_CHECK_LAUNCH(ctx, "gray3_flat_kernel");
         return DIP_OK;
     }
@@ -337,11 +334,30 @@ int launch_grayscale(dip_ctx* ctx, const ImgView& src, const ImgView& dst) {
     const size_t blocks = (total + kThreads - 1) / kThreads;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
     if (exact_rows(src) || exact_rows(dst))
-        DIP_CUDA(ctx, launch_kernel(gray3_kernel<true>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total));
+        DIP_CUDA(ctx, launch_kernel(gray3_kernel<true, MAPPED>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total, pre, post));
     else
-        DIP_CUDA(ctx, launch_kernel(gray3_kernel<false>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total));
+        DIP_CUDA(ctx, launch_kernel(gray3_kernel<false, MAPPED>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total, pre, post));
     DIP_CHECK_LAUNCH(ctx, "gray3_kernel");
     return DIP_OK;
+}
+
+}  // namespace
+
+int launch_grayscale(dip_ctx* ctx, const ImgView& src, const ImgView& dst) {
+    if (src.channels == 1) return launch_point_t<kCopy>(ctx, src, dst, MapParams{});
+    if (src.channels == 4) return launch_point_t<kGray4>(ctx, src, dst, MapParams{});
+    return launch_gray3<false>(ctx, src, dst, MapParams{}, MapParams{});
+}
+
+int launch_point_chain(dip_ctx* ctx, const ImgView& src, const ImgView& dst, const ByteMap& pre, bool gray, const ByteMap& post) {
+    if (!gray || src.channels == 1) {  // one-channel grayscale is the identity (cvtColor GRAY2GRAY)
+        const ByteMap m = pre.then(post);
+        if (m.identity()) return launch_point_t<kCopy>(ctx, src, dst, MapParams{});
+        return launch_point_t<kMap>(ctx, src, dst, map_params(m));
+    }
+    if (pre.identity() && post.identity()) return launch_grayscale(ctx, src, dst);
+    if (src.channels == 4) return launch_point_t<kMapGray4>(ctx, src, dst, map_params(pre), map_params(post));
+    return launch_gray3<true>(ctx, src, dst, map_params(pre), map_params(post));
 }
 
 int launch_synth(dip_ctx* ctx, const ImgView& dst, uint32_t seed, uint64_t first_row) {

@@ -245,6 +245,19 @@ class Context:
     def apply(self, op: capi.Op, src: Image, dst: Image):
         check(lib().dip_apply(self._h, C.byref(op), src._h, dst._h), self._h)
 
+    def apply_chain(self, ops, src: Image, dst: Image):
+        """dst = ops[-1](...ops[0](src)) in as few passes over HBM as the chain allows (dip_apply_chain)."""
+        arr = (capi.Op * len(ops))(*ops)
+        check(lib().dip_apply_chain(self._h, arr, len(ops), src._h, dst._h), self._h)
+
+    @staticmethod
+    def chain_passes(ops, channels: int = 3) -> int:
+        """Kernel launches dip_apply_chain makes for this chain (needs no GPU)."""
+        arr = (capi.Op * len(ops))(*ops)
+        n = C.c_int(0)
+        check(lib().dip_chain_passes(arr, len(ops), channels, C.byref(n)), None)
+        return n.value
+
     def apply_rows(self, op: capi.Op, src: Image, valid_row0: int, valid_rows: int, out_row0: int, out_rows: int,
                    dst: Image, dst_row0: int = 0):
         check(lib().dip_apply_rows(self._h, C.byref(op), src._h, valid_row0, valid_rows, out_row0, out_rows, dst._h,
@@ -330,6 +343,37 @@ def free_pinned(arr: np.ndarray) -> None:
 
 
 # (prefix, method name, extra args) in the reference's order -- opencv/benchmark.py:94-105
+OP_KINDS = {"copy": 0, "invert": 1, "grayscale": 2, "threshold": 3, "erode": 4, "erode_separable": 5, "convolve": 6,
+            "convolve_separable": 7, "gaussian_blur3x3": 8, "dilate": 9, "gauss5x5_erode3x3": 10}
+
+
+def make_op(kind: str, *, thresh: int = 0, maxval: int = 0, mask=None, mask_wh=None, kernel=None, kernel_col=None) -> capi.Op:
+    """A dip_op entry for dip_apply / dip_apply_chain (include/dip.h); the arrays stay referenced by the object."""
+    op = capi.Op()
+    op.kind = OP_KINDS[kind]
+    op.thresh, op.maxval = thresh, maxval
+    keep = []
+    if mask is not None:
+        m = np.ascontiguousarray(mask, dtype=np.uint8)
+        keep.append(m)
+        op.mask, op.mask_h, op.mask_w = m.ctypes.data, m.shape[0], m.shape[1]
+    if mask_wh is not None:
+        op.mask_w, op.mask_h = mask_wh
+    if kernel is not None:
+        k = np.ascontiguousarray(kernel, dtype=np.float32)
+        keep.append(k)
+        op.kernel = k.ctypes.data
+        if kernel_col is None:
+            k2 = np.atleast_2d(k)
+            op.kh, op.kw = k2.shape
+        else:
+            kc = np.ascontiguousarray(kernel_col, dtype=np.float32)
+            keep.append(kc)
+            op.kernel_col, op.kw, op.kh = kc.ctypes.data, k.size, kc.size
+    op._keep = keep
+    return op
+
+
 REFERENCE_OPS = [
     ("copy", "copy", ()),
     ("inversion", "invert", ()),

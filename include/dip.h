@@ -189,6 +189,22 @@ typedef struct dip_op {
 /* dst = op(src) for one entry of an operation list */
 DIP_API int dip_apply(dip_ctx* ctx, const dip_op* op, const dip_image* src, dip_image* dst);
 
+/* Op chain: dst = ops[n-1]( ... ops[1]( ops[0](src) ) ), bit for bit what n dip_apply calls
+ * through intermediate images give -- the reference's separable pairs through `aux` (opencv:76-90) are its two-op
+ * instance -- in as few passes over HBM as the chain allows:
+ *   - runs of byte-wise ops (copy, inversion, threshold) collapse into ONE per-byte map (identity, 255 - x or a step);
+ *   - that map is fused into the neighbouring tiled stencil kernel (applied to the result, or to the source words, in
+ *     registers; in front of an erosion / dilation it moves behind it, min / max commuting with monotone maps) or
+ *     into the grayscale kernel, so it costs no pass of its own;
+ *   - 5x5 Gaussian followed directly by 3x3 square erosion runs as the fused dip_gauss5x5_erode3x3 kernel;
+ *   - every other stencil, and every grayscale, is one pass.
+ * e.g. grayscale -> GaussianBlur -> threshold -> erode: 3 passes (gray | blur+threshold | erode) instead of 4.
+ * Intermediate results live in one scratch stack owned by the ctx (allocated on first use, same shape as src) and in
+ * dst.  src and dst must not overlap unless the whole chain is byte-wise / grayscale. */
+DIP_API int dip_apply_chain(dip_ctx* ctx, const dip_op* ops, int n, const dip_image* src, dip_image* dst);
+/* number of kernel launches (= passes over HBM) dip_apply_chain makes for this chain on `channels`-channel images */
+DIP_API int dip_chain_passes(const dip_op* ops, int n, int channels, int* passes);
+
 /* Fill `ops` (capacity >= 12) with the reference's 12 device operations in its order:
  * copy, inversion, grayscale, threshold(127,255), erosion cross / square / 1x3+3x1,
  * convolution 3x3 / 1x3+3x1 / 5x5 / 1x5+5x1 Gaussian, GaussianBlur 3x3.  Mask and kernel

@@ -84,3 +84,23 @@ def test_bench_reference_arm_prints_one_json_line():
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "Mpixel/s" and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+
+
+def test_chain_planner_counts_passes_without_a_gpu():
+    """dip_chain_passes is host logic: byte-wise runs fold into one map that rides on a neighbouring tiled kernel."""
+    import numpy as np
+    from dip_benchmark_b200 import Context, make_op
+    cross = np.array([[0, 1, 0], [1, 1, 1], [0, 1, 0]], np.uint8)
+    g5 = np.outer([1, 4, 6, 4, 1], [1, 4, 6, 4, 1]).astype(np.float32) / 256
+    ops = {"gray": make_op("grayscale"), "inv": make_op("invert"), "thr": make_op("threshold", thresh=127, maxval=255),
+           "erode": make_op("erode", mask=np.ones((3, 3), np.uint8)), "cross": make_op("erode", mask=cross),
+           "tall": make_op("erode", mask=np.ones((5, 3), np.uint8)), "g5": make_op("convolve", kernel=g5),
+           "blur": make_op("gaussian_blur3x3")}
+    def passes(names, c=3):
+        return Context.chain_passes([ops[n] for n in names], c)
+    assert passes(["gray", "blur", "thr", "erode"]) == 3          # gray | blur+threshold | erode (4 reference calls)
+    assert passes(["thr", "cross", "inv"]) == 1
+    assert passes(["inv", "thr", "inv", "thr"]) == 1
+    assert passes(["g5", "erode"]) == 1                            # the fused Gaussian+erosion kernel
+    assert passes(["inv", "tall", "thr"]) == 3                     # direct kernels take no maps
+    assert passes(["gray", "inv", "gray"], 3) == 1 and passes(["gray", "inv", "gray"], 4) == 2 and passes(["gray", "inv", "gray"], 1) == 1

@@ -598,3 +598,131 @@ def test_pipeline_host_rings_and_point_op_row_ranges(ctx, dip, orc):
     want[5:25] = 255 - img[10:30]
     assert np.array_equal(got, want)
     src.close(); dst.close()
+
+
+# ---- op chains (dip_apply_chain) ------------------------------------------------------------
+def _chain_pool(dip, orc):
+    """name -> (dip_op, oracle function on one HxWxC frame)"""
+    mk = dip.ops.make_op
+    tall = np.ones((5, 3), np.uint8); tall[0, 0] = 0                      # not a tiled kernel: direct path
+    box = np.full((3, 3), 1.0 / 8.0, np.float32); box[1, 1] = 0.0           # dyadic, not Gaussian: direct path
+    return {
+        "copy": (mk("copy"), orc.copy),
+        "invert": (mk("invert"), orc.invert),
+        "gray": (mk("grayscale"), orc.grayscale),
+        "thr": (mk("threshold", thresh=127, maxval=255), lambda im: orc.threshold(im, 127, 255)),
+        "thr60": (mk("threshold", thresh=60, maxval=200), lambda im: orc.threshold(im, 60, 200)),
+        "thr255": (mk("threshold", thresh=255, maxval=9), lambda im: orc.threshold(im, 255, 9)),
+        "thr0": (mk("threshold", thresh=0, maxval=1), lambda im: orc.threshold(im, 0, 1)),
+        "erode_cross": (mk("erode", mask=orc.CROSS_MASK), lambda im: orc.erode(im, orc.CROSS_MASK)),
+        "erode_sq": (mk("erode", mask=orc.SQUARE_MASK), lambda im: orc.erode(im, orc.SQUARE_MASK)),
+        "erode_sep": (mk("erode_separable", mask_wh=(3, 3)), orc.erode_separable),
+        "erode_tall": (mk("erode", mask=tall), lambda im: orc.erode(im, tall)),
+        "dilate_cross": (mk("dilate", mask=orc.CROSS_MASK), lambda im: orc.dilate(im, orc.CROSS_MASK)),
+        "dilate_sq": (mk("dilate", mask=orc.SQUARE_MASK), lambda im: orc.dilate(im, orc.SQUARE_MASK)),
+        "conv3": (mk("convolve", kernel=orc.BLUR_3X3), lambda im: orc.filter2d(im, orc.BLUR_3X3)),
+        "conv3sep": (mk("convolve_separable", kernel=orc.BLUR_3X3_1X3, kernel_col=orc.BLUR_3X3_3X1),
+                     lambda im: orc.filter2d_separable(im, orc.BLUR_3X3_1X3, orc.BLUR_3X3_3X1)),
+        "conv5": (mk("convolve", kernel=orc.BLUR_5X5), lambda im: orc.filter2d(im, orc.BLUR_5X5)),
+        "conv5sep": (mk("convolve_separable", kernel=orc.BLUR_5X5_1X5, kernel_col=orc.BLUR_5X5_5X1),
+                     lambda im: orc.filter2d_separable(im, orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1)),
+        "row3": (mk("convolve", kernel=orc.BLUR_3X3_1X3), lambda im: orc.filter2d(im, orc.BLUR_3X3_1X3)),
+        "box": (mk("convolve", kernel=box), lambda im: orc.filter2d(im, box)),
+        "gauss3": (mk("gaussian_blur3x3"), orc.gaussian_blur3x3),
+        "g5e3": (mk("gauss5x5_erode3x3"), lambda im: orc.erode(orc.filter2d(im, orc.BLUR_5X5), orc.SQUARE_MASK)),
+    }
+
+
+def _run_chain(ctx, pool, names, stack):
+    src = ctx.from_array(stack)
+    dst = ctx.image_like(src)
+    ctx.apply_chain([pool[n][0] for n in names], src, dst)
+    got = dst.download().reshape(stack.shape)
+    assert np.array_equal(src.download().reshape(stack.shape), stack), "the chain modified its source"
+    src.close(); dst.close()
+    want = stack.copy()
+    for f in range(stack.shape[0]):
+        im = stack[f]
+        for n in names:
+            im = pool[n][1](im)
+        want[f] = im
+    return got, want
+
+
+CHAINS = [  # (ops, passes on 3 channels)
+    (["gray", "gauss3", "thr", "erode_sq"], 3),            # SURVEY.md 8f rank 4's example: gray | blur+threshold | erode
+    (["thr", "erode_cross", "invert"], 1),
+    (["invert", "conv5", "erode_sq", "thr60"], 3),         # point | fused Gaussian+erosion | point
+    (["invert", "thr60", "invert", "copy"], 1),
+    (["gray", "invert", "gray"], 1),
+    (["conv3sep", "invert", "conv5sep", "thr60", "gray"], 3),
+    (["thr", "erode_tall", "invert", "dilate_cross"], 3),  # direct kernel takes no maps; the next tiled one takes `invert`
+    (["gray", "thr", "erode_sep"], 2),
+    (["conv5"], 1),
+    (["copy"], 1),
+    (["copy", "copy", "conv3"], 1),
+    (["invert", "thr255", "dilate_sq", "thr0", "invert"], 1),
+    (["g5e3", "invert", "row3"], 2),
+    (["box", "thr", "gray", "invert", "conv5sep", "conv3", "gauss3"], 5),
+    (["erode_sq", "dilate_sq", "erode_cross", "dilate_cross"], 4),
+]
+
+
+def test_chain_plans_and_results_equal_sequential_application(ctx, dip, orc):
+    pool = _chain_pool(dip, orc)
+    rng = np.random.default_rng(77)
+    for names, passes in CHAINS:
+        assert dip.Context.chain_passes([pool[n][0] for n in names], 3) == passes, names
+        for c, (h, w), n in [(3, (70, 200), 2), (1, (61, 515), 1), (4, (37, 129), 1), (3, (2, 3), 1)]:
+            stack = np.stack([rand_img(rng, h, w, c) for _ in range(n)])
+            before = ctx.launch_count()
+            got, want = _run_chain(ctx, pool, names, stack)
+            assert np.array_equal(got, want), (names, c, h, w)
+            launched = ctx.launch_count() - before
+            assert launched == dip.Context.chain_passes([pool[n_][0] for n_ in names], c), (names, c, launched)
+
+
+def test_random_chains(ctx, dip, orc):
+    pool = _chain_pool(dip, orc)
+    names_all = sorted(pool)
+    rng = np.random.default_rng(4242)
+    for trial in range(60):
+        k = int(rng.integers(1, 7))
+        names = [names_all[int(i)] for i in rng.integers(0, len(names_all), k)]
+        c = int(rng.choice([1, 3, 4])); h = int(rng.choice([1, 4, 17, 60, 61, 97])); w = int(rng.choice([1, 7, 170, 171, 400]))
+        n = int(rng.choice([1, 1, 3]))
+        stack = np.stack([rand_img(rng, h, w, c) for _ in range(n)])
+        got, want = _run_chain(ctx, pool, names, stack)
+        assert np.array_equal(got, want), f"trial {trial}: {names} on {n}x{h}x{w}x{c}"
+
+
+def test_byte_map_composition_on_all_values(ctx, dip):
+    """Every composition of inversions and thresholds is one per-byte map: check it on all 256 values (and in place)."""
+    mk = dip.ops.make_op
+    rng = np.random.default_rng(5)
+    ramp = np.arange(256, dtype=np.uint8).reshape(1, 16, 16, 1).repeat(3, axis=3)
+    for trial in range(300):
+        ops, want = [], ramp.copy()
+        for _ in range(int(rng.integers(1, 7))):
+            if rng.random() < 0.45:
+                ops.append(mk("invert")); want = 255 - want
+            else:
+                t = int(rng.choice([0, 1, 126, 127, 128, 254, 255, int(rng.integers(0, 256))])); m = int(rng.choice([0, 1, 255, int(rng.integers(0, 256))]))
+                ops.append(mk("threshold", thresh=t, maxval=m)); want = np.where(want > t, m, 0).astype(np.uint8)
+        assert dip.Context.chain_passes(ops, 3) == 1
+        img = ctx.from_array(ramp)
+        ctx.apply_chain(ops, img, img)  # byte-wise chains may run in place
+        assert np.array_equal(img.download().reshape(ramp.shape), want), trial
+        img.close()
+
+
+def test_chain_errors(ctx, dip, orc):
+    pool = _chain_pool(dip, orc)
+    img = ctx.from_array(np.zeros((1, 8, 8, 3), np.uint8))
+    with pytest.raises(dip.DipError):
+        ctx.apply_chain([pool["invert"][0], pool["conv3"][0]], img, img)       # stencils cannot run in place
+    bad = dip.ops.make_op("copy"); bad.kind = 99
+    other = ctx.image_like(img)
+    with pytest.raises(dip.DipError):
+        ctx.apply_chain([bad], img, other)
+    img.close(); other.close()
