@@ -482,12 +482,44 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
     }
 }
 
+// Everything after the tile has landed in shared memory: border patching, then each warp's band.  Block-uniform
+// control flow around the barriers (threads without a column / band skip the arithmetic, not the function).
+template <int OP, int C, int R, int kWarps, bool MAPPED>
+__device__ __forceinline__ void process_tile(uint8_t* tile, const StencilParams& p, int tx, int ty, int f) {
+    constexpr int r = op_radius_y(OP);   // halo rows
+    constexpr int rx = op_radius_x(OP);  // halo pixels
+    constexpr int kThreads = kWarps * 32;
+    constexpr int TH = kWarps * R;
+    constexpr int ROWS = TH + 2 * r;
+    const int bx0 = tx * kTileBytes;
+    const int y0 = p.out_y0 + ty * TH;  // first output row of the tile
+    const int ytop = y0 - r;            // source row held by tile row 0
+    const bool border = (rx > 0 && (bx0 == 0 || bx0 + kTileBytes + rx * C > p.rowbytes)) ||
+                        (r > 0 && (ytop < p.valid_y0 || ytop + ROWS > p.valid_y1));
+    if (border) {
+        __syncthreads();
+        patch_borders<OP, C, ROWS, kThreads>(tile, p, bx0, ytop);
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cx = bx0 + 16 * lane;  // first byte of this thread's column
+    const int yw = y0 + warp * R;    // first output row of this warp
+    if (cx >= ((p.rowbytes + 15) & ~15) || yw >= p.out_y1) return;
+    const int nrows = min(R, p.out_y1 - yw);
+    const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // tile row of source row yw - r
+    uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
+
+    // warp-uniform: does this tile column contain the partial last chunk of an unpadded destination row?
+    const bool clip = p.dst_exact && bx0 + kTileBytes > p.rowbytes && (p.rowbytes & 15) != 0;
+    if (clip) compute_band<OP, C, R, false, true, MAPPED>(colp, dptr, p, nrows, cx);
+    else if (nrows == R) compute_band<OP, C, R, true, false, MAPPED>(colp, dptr, p, R, cx);
+    else compute_band<OP, C, R, false, false, MAPPED>(colp, dptr, p, nrows, cx);
+}
+
 // ---- the tiled kernel -------------------------------------------------------------------------
 template <int OP, int C, int R, int kWarps, bool MAPPED>
 __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
     constexpr int r = op_radius_y(OP);   // halo rows
-    constexpr int rx = op_radius_x(OP);  // halo pixels
-    constexpr int kThreads = kWarps * 32;
     constexpr int TH = kWarps * R;
     constexpr int ROWS = TH + 2 * r;
     extern __shared__ __align__(128) uint8_t smem[];
@@ -510,28 +542,9 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
     __syncthreads();  // barrier init visible to the waiters
     mbar_wait(bar, 0);
 
-    const bool border = (rx > 0 && (bx0 == 0 || bx0 + kTileBytes + rx * C > p.rowbytes)) ||
-                        (r > 0 && (ytop < p.valid_y0 || ytop + ROWS > p.valid_y1));
-    if (border) {
-        __syncthreads();
-        patch_borders<OP, C, ROWS, kThreads>(tile, p, bx0, ytop);
-    }
-
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int cx = bx0 + 16 * lane;  // first byte of this thread's column
-    if (cx >= ((p.rowbytes + 15) & ~15)) return;
-    const int yw = y0 + warp * R;    // first output row of this warp
-    if (yw >= p.out_y1) return;
-    const int nrows = min(R, p.out_y1 - yw);
-    const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // tile row of source row yw - r
-    uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
-
-    // warp-uniform: does this tile column contain the partial last chunk of an unpadded destination row?
-    const bool clip = p.dst_exact && bx0 + kTileBytes > p.rowbytes && (p.rowbytes & 15) != 0;
-    if (clip) compute_band<OP, C, R, false, true, MAPPED>(colp, dptr, p, nrows, cx);
-    else if (nrows == R) compute_band<OP, C, R, true, false, MAPPED>(colp, dptr, p, R, cx);
-    else compute_band<OP, C, R, false, false, MAPPED>(colp, dptr, p, nrows, cx);
+    process_tile<OP, C, R, kWarps, MAPPED>(tile, p, tx, ty, f);
 }
+
 template <int OP, int C, int R, int kWarps, bool MAPPED>
 int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps) {
     constexpr int r = op_radius_y(OP);
