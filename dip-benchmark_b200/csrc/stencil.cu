@@ -42,6 +42,85 @@ namespace {
 struct Knobs { int tile_rows = 0, fused_rows = 0; };
 Knobs g_knobs;
 
+// One warp band of the fused Gaussian -> erosion kernel below.  EDGE: the tile touches the image rim, so Gaussian
+// values outside the image count as 255 (+inf) for the erosion; CLIP: partial last chunk of an unpadded row.
+template <int C, int R, bool EDGE, bool CLIP, bool FULL>
+__device__ __forceinline__ void fused_band(const uint8_t* colp, const StencilParams& p, int cx, int yw, int f, int lane) {
+    const int n_out = FULL ? R : min(R, p.out_y1 - yw);  // FULL: compile-time trip count (no remainder loop)
+    // Gaussian bytes outside [0, rowbytes) count as 255 for the erosion: per-lane masks in packed form
+    uint32_t colmask[8];
+    if constexpr (EDGE) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int b0 = cx + 4 * j;
+            auto out = [&](int pos) { return (pos < 0 || pos >= p.rowbytes) ? 0xFF00u : 0u; };
+            colmask[2 * j] = out(b0) | (out(b0 + 2) << 16);
+            colmask[2 * j + 1] = out(b0 + 1) | (out(b0 + 3) << 16);
+        }
+    }
+    const bool store_lane = lane != 0 && lane != 31 && cx < ((p.rowbytes + 15) & ~15);
+    const int valid = CLIP ? p.rowbytes - cx : 16;
+    uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
+    const uint32_t vbias = reg_const<0x007F007Fu>();
+
+    Acc8 h0, h1, h2, h3, h4;  // horizontal Gaussian passes of five consecutive source rows
+    Acc8 m0, m1;              // horizontal minima of the two previous Gaussian rows
+    Row8 row;
+    auto hpass = [&](const uint8_t* rp, Acc8& h) {
+        load_row(rp, row);
+        hsum5<C>(row, h, 0u);
+    };
+    // Gaussian row g (image row yw - 1 + g) from the window, then its horizontal 3-minimum
+    auto gauss_hmin = [&](int g, Acc8& hm) {
+        uint32_t rowmask = 0u;
+        if constexpr (EDGE) {
+            const int yg = yw - 1 + g;
+            rowmask = (yg >= p.valid_y0 && yg < p.valid_y1) ? 0u : 0xFF00FF00u;
+        }
+        Row8 gr;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            // one ALU-pipe add, three IMADs (this kernel is ALU-pipe bound: PRMT funnels, VIMNMX3, rounding)
+            uint32_t v = rne_finish((h0.v[k] + h4.v[k]) + (4u * padd(h1.v[k], h3.v[k]) + (6u * h2.v[k] + vbias)));
+            if constexpr (EDGE) v |= colmask[k] | rowmask;
+            if (k & 1) gr.o[2 + (k >> 1)] = v; else gr.e[2 + (k >> 1)] = v;
+        }
+        gr.e[1] = __shfl_up_sync(0xFFFFFFFFu, gr.e[5], 1);
+        gr.o[1] = __shfl_up_sync(0xFFFFFFFFu, gr.o[5], 1);
+        gr.e[6] = __shfl_down_sync(0xFFFFFFFFu, gr.e[2], 1);
+        gr.o[6] = __shfl_down_sync(0xFFFFFFFFu, gr.o[2], 1);
+        gr.e[0] = gr.o[0] = gr.e[7] = gr.o[7] = 0u;  // outside a 3-tap's reach
+        hmnmx3<C, false>(gr, hm);
+    };
+    hpass(colp, h0);
+    hpass(colp + kRowBytes, h1);
+    hpass(colp + 2 * kRowBytes, h2);
+    hpass(colp + 3 * kRowBytes, h3);
+    hpass(colp + 4 * kRowBytes, h4);
+    gauss_hmin(0, m0);
+    h0 = h1; h1 = h2; h2 = h3; h3 = h4;
+    hpass(colp + 5 * kRowBytes, h4);
+    gauss_hmin(1, m1);
+    h0 = h1; h1 = h2; h2 = h3; h3 = h4;
+#pragma unroll 5
+    for (int i = 0; i < n_out; ++i) {
+        hpass(colp + (i + 6) * kRowBytes, h4);
+        Acc8 m2;
+        gauss_hmin(i + 2, m2);
+        if (store_lane) {
+            uint32_t out[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+                out[j] = pack_hi(mnmx3<false>(m0.v[2 * j], m1.v[2 * j], m2.v[2 * j]), mnmx3<false>(m0.v[2 * j + 1], m1.v[2 * j + 1], m2.v[2 * j + 1]));
+            const uint4 o = make_uint4(out[0], out[1], out[2], out[3]);
+            if constexpr (CLIP) store16(dptr + (size_t)i * p.dst.pitch, o, valid);
+            else __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch), o);
+        }
+        m0 = m1; m1 = m2;
+        h0 = h1; h1 = h2; h2 = h3; h3 = h4;
+    }
+}
+
 // =================================================================================================
 // Fused chain: 5x5 Gaussian (filter2D semantics, reflect-101, RNE) followed by 3x3 square erosion
 // (+inf border) in ONE kernel -- BASELINE.json config 5's pipeline at 2 bytes of HBM traffic per pixel
@@ -90,72 +169,13 @@ __global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_co
     const int cx = gx0 + 16 * lane;       // first byte of this thread's column
     const int yw = y0 + warp * R;         // first output row of this warp
     if (yw >= p.out_y1) return;           // whole warp
-    const int n_out = min(R, p.out_y1 - yw);
-    // Gaussian bytes outside [0, rowbytes) count as 255 for the erosion: per-lane masks in packed form
-    uint32_t colmask[8];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const int b0 = cx + 4 * j;
-        auto out = [&](int pos) { return (pos < 0 || pos >= p.rowbytes) ? 0xFF00u : 0u; };
-        colmask[2 * j] = out(b0) | (out(b0 + 2) << 16);
-        colmask[2 * j + 1] = out(b0 + 1) | (out(b0 + 3) << 16);
-    }
     const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // source row yw - 3
-    const bool store_lane = lane != 0 && lane != 31 && cx < ((p.rowbytes + 15) & ~15);
-    const bool clip = p.dst_exact && gx0 + kTileBytes > p.rowbytes && (p.rowbytes & 15) != 0;  // block-uniform
-    const int valid = clip ? p.rowbytes - cx : 16;
-    uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
-
-    Acc8 h0, h1, h2, h3, h4;  // horizontal Gaussian passes of five consecutive source rows
-    Acc8 m0, m1;              // horizontal minima of the two previous Gaussian rows
-    Row8 row;
-    auto hpass = [&](const uint8_t* rp, Acc8& h) {
-        load_row(rp, row);
-        hsum5<C>(row, h, 0u);
-    };
-    // Gaussian row g (image row yw - 1 + g) from the window, then its horizontal 3-minimum
-    auto gauss_hmin = [&](int g, Acc8& hm) {
-        const int yg = yw - 1 + g;
-        const uint32_t rowmask = (yg >= p.valid_y0 && yg < p.valid_y1) ? 0u : 0xFF00FF00u;
-        Row8 gr;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) {
-            const uint32_t v = rne_finish((h0.v[k] + h4.v[k] + 0x007F007Fu) + 4u * (h1.v[k] + h3.v[k]) + 6u * h2.v[k]) | colmask[k] | rowmask;
-            if (k & 1) gr.o[2 + (k >> 1)] = v; else gr.e[2 + (k >> 1)] = v;
-        }
-        gr.e[1] = __shfl_up_sync(0xFFFFFFFFu, gr.e[5], 1);
-        gr.o[1] = __shfl_up_sync(0xFFFFFFFFu, gr.o[5], 1);
-        gr.e[6] = __shfl_down_sync(0xFFFFFFFFu, gr.e[2], 1);
-        gr.o[6] = __shfl_down_sync(0xFFFFFFFFu, gr.o[2], 1);
-        gr.e[0] = gr.o[0] = gr.e[7] = gr.o[7] = 0u;  // outside a 3-tap's reach
-        hmnmx3<C, false>(gr, hm);
-    };
-    hpass(colp, h0);
-    hpass(colp + kRowBytes, h1);
-    hpass(colp + 2 * kRowBytes, h2);
-    hpass(colp + 3 * kRowBytes, h3);
-    hpass(colp + 4 * kRowBytes, h4);
-    gauss_hmin(0, m0);
-    h0 = h1; h1 = h2; h2 = h3; h3 = h4;
-    hpass(colp + 5 * kRowBytes, h4);
-    gauss_hmin(1, m1);
-    h0 = h1; h1 = h2; h2 = h3; h3 = h4;
-    const int n_loop = (n_out == R) ? R : n_out;
-#pragma unroll 5
-    for (int i = 0; i < n_loop; ++i) {
-        hpass(colp + (i + 6) * kRowBytes, h4);
-        Acc8 m2;
-        gauss_hmin(i + 2, m2);
-        if (store_lane) {
-            uint32_t out[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j)
-                out[j] = pack_hi(mnmx3<false>(m0.v[2 * j], m1.v[2 * j], m2.v[2 * j]), mnmx3<false>(m0.v[2 * j + 1], m1.v[2 * j + 1], m2.v[2 * j + 1]));
-            store16(dptr + (size_t)i * p.dst.pitch, make_uint4(out[0], out[1], out[2], out[3]), valid);
-        }
-        m0 = m1; m1 = m2;
-        h0 = h1; h1 = h2; h2 = h3; h3 = h4;
-    }
+    const bool clip = p.dst_exact && gx0 + kTileBytes > p.rowbytes && (p.rowbytes & 15) != 0;  // block-uniform, implies border
+    // interior tiles (all but the image's rim) run the variant without the out-of-image masks
+    if (clip) fused_band<C, R, true, true, false>(colp, p, cx, yw, f, lane);
+    else if (border) fused_band<C, R, true, false, false>(colp, p, cx, yw, f, lane);
+    else if (yw + R <= p.out_y1) fused_band<C, R, false, false, true>(colp, p, cx, yw, f, lane);
+    else fused_band<C, R, false, false, false>(colp, p, cx, yw, f, lane);
 }
 
 template <int C, int R, int kWarps>
