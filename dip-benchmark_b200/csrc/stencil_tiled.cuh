@@ -111,6 +111,11 @@ __device__ __forceinline__ uint32_t reg_const() {
 }
 __constant__ uint32_t c_one = 1u;
 __device__ __forceinline__ uint32_t padd(uint32_t a, uint32_t b) { return a * c_one + b; }  // add on the FMA pipe
+// x * 2^k + y as ONE IMAD.  With an immediate power of two ptxas prefers LEA / IADD3 (ALU pipe) or IMAD.SHL + VIADD
+// (two instructions) whatever the source says; a multiplier it cannot see keeps the multiply-add on the FMA pipe.
+__constant__ uint32_t c_pow2[6] = {1u, 2u, 4u, 8u, 16u, 32u};
+template <int LOG2>
+__device__ __forceinline__ uint32_t shl_add(uint32_t x, uint32_t y) { return x * c_pow2[LOG2] + y; }
 
 __device__ __forceinline__ uint32_t odd_bytes(uint32_t w) { return __byte_perm(w, 0u, 0x4341); }   // (b1, b3): PRMT
 __device__ __forceinline__ uint32_t even_bytes(uint32_t w, uint32_t odd) { return w - odd * 256u; } // (b0, b2): IMAD
@@ -152,8 +157,8 @@ struct Acc8 {
 template <int C>
 __device__ __forceinline__ void hsum3(const Row8& r, Acc8& h, uint32_t bias) {
 #define DIP_H3(j)                                                                                     \
-    h.v[2 * j] = padd(pair_at<4 * j - C>(r), padd(pair_at<4 * j + C>(r), 2u * r.e[2 + j] + bias));    \
-    h.v[2 * j + 1] = padd(pair_at<4 * j + 1 - C>(r), padd(pair_at<4 * j + 1 + C>(r), 2u * r.o[2 + j] + bias));
+    h.v[2 * j] = padd(pair_at<4 * j - C>(r), padd(pair_at<4 * j + C>(r), shl_add<1>(r.e[2 + j], bias)));    \
+    h.v[2 * j + 1] = padd(pair_at<4 * j + 1 - C>(r), padd(pair_at<4 * j + 1 + C>(r), shl_add<1>(r.o[2 + j], bias)));
     DIP_H3(0) DIP_H3(1) DIP_H3(2) DIP_H3(3)
 #undef DIP_H3
 }
@@ -434,11 +439,9 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
             for (int k = 0; k < 8; ++k) {
                 // V = h0 + 2 h1 + h2 <= 4080 (both variants); X = 16 V has the result in the high byte
                 const uint32_t u = padd(h0.v[k], h2.v[k]);
-                if constexpr (OP == kGauss3) {
-                    res[k] = u * 16u + (h1.v[k] * 32u + vbias);              // (S + 8) >> 4
-                } else {
-                    res[k] = rne_finish(u * 16u + (h1.v[k] * 32u + vbias));
-                }
+                const uint32_t x = shl_add<4>(u, shl_add<5>(h1.v[k], vbias));
+                if constexpr (OP == kGauss3) res[k] = x;                     // (S + 8) >> 4
+                else res[k] = rne_finish(x);
             }
             put16<CLIP, MAPPED>(dptr + (size_t)i * p.dst.pitch,
                     make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7])), valid, p);
