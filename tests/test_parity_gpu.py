@@ -686,7 +686,7 @@ def test_random_chains(ctx, dip, orc):
     pool = _chain_pool(dip, orc)
     names_all = sorted(pool)
     rng = np.random.default_rng(4242)
-    for trial in range(60):
+    for trial in range(200):
         k = int(rng.integers(1, 7))
         names = [names_all[int(i)] for i in rng.integers(0, len(names_all), k)]
         c = int(rng.choice([1, 3, 4])); h = int(rng.choice([1, 4, 17, 60, 61, 97])); w = int(rng.choice([1, 7, 170, 171, 400]))
