@@ -110,6 +110,7 @@ def lib() -> C.CDLL:
         "dip_apply": ([vp, P(Op), vp, vp], i),
         "dip_apply_chain": ([vp, P(Op), i, vp, vp], i),
         "dip_chain_passes": ([P(Op), i, i, P(i)], i),
+        "dip_chain_lut": ([P(Op), i, P(u8)], i),
         "dip_reference_ops": ([P(Op), i], i),
         "dip_reference_op_prefix": ([i], C.c_char_p),
         "dip_reference_op_description": ([i], C.c_char_p),

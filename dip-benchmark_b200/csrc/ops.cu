@@ -245,6 +245,17 @@ int dip_chain_passes(const dip_op* ops, int n, int channels, int* passes) {
     return DIP_OK;
 }
 
+int dip_chain_lut(const dip_op* ops, int n, uint8_t lut[256]) {
+    if (!ops || n < 1 || !lut) return fail(nullptr, DIP_ERR_ARG, "bad argument");
+    ByteMap m;
+    for (int i = 0; i < n; ++i) {
+        if (!is_byte_op(ops[i].kind)) return fail(nullptr, DIP_ERR_ARG, "operation %d (kind %d) is not byte-wise", i, ops[i].kind);
+        m = m.then(ops[i].kind == DIP_OP_INVERT ? ByteMap::invert() : ops[i].kind == DIP_OP_THRESHOLD ? ByteMap::step(ops[i].thresh, ops[i].maxval, 0) : ByteMap{});
+    }
+    for (int x = 0; x < 256; ++x) lut[x] = m.eval((uint8_t)x);
+    return DIP_OK;
+}
+
 int dip_apply_chain(dip_ctx* ctx, const dip_op* ops, int n, const dip_image* src, dip_image* dst) {
     if (!ctx || !ops || n < 1) return fail(ctx, DIP_ERR_ARG, "bad argument");
     int rc = check_pair(ctx, src, dst, true);

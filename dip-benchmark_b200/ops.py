@@ -258,6 +258,14 @@ class Context:
         check(lib().dip_chain_passes(arr, len(ops), channels, C.byref(n)), None)
         return n.value
 
+    @staticmethod
+    def chain_lut(ops) -> np.ndarray:
+        """The per-byte map a run of copy / inversion / threshold ops folds into, as a 256-entry table (needs no GPU)."""
+        arr = (capi.Op * len(ops))(*ops)
+        lut = (C.c_uint8 * 256)()
+        check(lib().dip_chain_lut(arr, len(ops), lut), None)
+        return np.frombuffer(lut, dtype=np.uint8).copy()
+
     def apply_rows(self, op: capi.Op, src: Image, valid_row0: int, valid_rows: int, out_row0: int, out_rows: int,
                    dst: Image, dst_row0: int = 0):
         check(lib().dip_apply_rows(self._h, C.byref(op), src._h, valid_row0, valid_rows, out_row0, out_rows, dst._h,

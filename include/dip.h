@@ -204,6 +204,9 @@ DIP_API int dip_apply(dip_ctx* ctx, const dip_op* op, const dip_image* src, dip_
 DIP_API int dip_apply_chain(dip_ctx* ctx, const dip_op* ops, int n, const dip_image* src, dip_image* dst);
 /* number of kernel launches (= passes over HBM) dip_apply_chain makes for this chain on `channels`-channel images */
 DIP_API int dip_chain_passes(const dip_op* ops, int n, int channels, int* passes);
+/* The single per-byte map a run of byte-wise ops (copy, inversion, threshold only) folds into, tabulated:
+ * lut[x] = ops[n-1](...ops[0](x)).  Host-only (no GPU needed); this is the map the kernels evaluate. */
+DIP_API int dip_chain_lut(const dip_op* ops, int n, uint8_t lut[256]);
 
 /* Fill `ops` (capacity >= 12) with the reference's 12 device operations in its order:
  * copy, inversion, grayscale, threshold(127,255), erosion cross / square / 1x3+3x1,

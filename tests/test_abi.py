@@ -104,3 +104,38 @@ def test_chain_planner_counts_passes_without_a_gpu():
     assert passes(["g5", "erode"]) == 1                            # the fused Gaussian+erosion kernel
     assert passes(["inv", "tall", "thr"]) == 3                     # direct kernels take no maps
     assert passes(["gray", "inv", "gray"], 3) == 1 and passes(["gray", "inv", "gray"], 4) == 2 and passes(["gray", "inv", "gray"], 1) == 1
+
+
+def test_byte_wise_runs_fold_into_one_exact_map():
+    """ByteMap composition (the host logic behind dip_apply_chain) against numpy on all 256 values: 2000 random runs
+    plus every pair of thresholds at the edge values."""
+    import numpy as np
+    import pytest
+    from dip_benchmark_b200 import Context, DipError, make_op
+    x = np.arange(256, dtype=np.uint8)
+    rng = np.random.default_rng(11)
+    edge = [0, 1, 126, 127, 128, 254, 255]
+    def run(seq):
+        ops, want = [], x.copy()
+        for kind, t, m in seq:
+            if kind == "inv":
+                ops.append(make_op("invert")); want = 255 - want
+            elif kind == "copy":
+                ops.append(make_op("copy"))
+            else:
+                ops.append(make_op("threshold", thresh=t, maxval=m)); want = np.where(want > t, m, 0).astype(np.uint8)
+        assert np.array_equal(Context.chain_lut(ops), want), seq
+    for _ in range(2000):
+        seq = []
+        for _ in range(int(rng.integers(1, 8))):
+            r = rng.random()
+            seq.append(("inv", 0, 0) if r < 0.4 else ("copy", 0, 0) if r < 0.5 else
+                       ("thr", int(rng.choice(edge + [int(rng.integers(0, 256))])), int(rng.choice(edge + [int(rng.integers(0, 256))]))))
+        run(seq)
+    for t1 in edge:
+        for m1 in edge:
+            for t2 in edge:
+                run([("thr", t1, m1), ("inv", 0, 0), ("thr", t2, 200), ("inv", 0, 0)])
+                run([("inv", 0, 0), ("thr", t1, m1), ("thr", t2, 77)])
+    with pytest.raises(DipError):
+        Context.chain_lut([make_op("grayscale")])
