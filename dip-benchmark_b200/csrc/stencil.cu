@@ -505,6 +505,7 @@ int dip_debug_set(const char* key, int value) {
     if (!key) return fail(nullptr, DIP_ERR_ARG, "null key");
     if (!strcmp(key, "tile_rows")) g_knobs.tile_rows = value;
     else if (!strcmp(key, "fused_rows")) g_knobs.fused_rows = value;
+    else if (!strcmp(key, "no_pad")) g_no_occupancy_pad = value != 0;
     else return fail(nullptr, DIP_ERR_ARG, "unknown knob %s", key);
     return DIP_OK;
 }

@@ -548,6 +548,8 @@ __global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_const
     process_tile<OP, C, R, kWarps, MAPPED>(tile, p, tx, ty, f);
 }
 
+bool g_no_occupancy_pad = false;  // development knob "no_pad"
+
 template <int OP, int C, int R, int kWarps, bool MAPPED>
 int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps) {
     constexpr int r = op_radius_y(OP);
@@ -561,7 +563,7 @@ int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGe
     constexpr int kCtasPerSm = R != 15 ? 0 : (OP == kErodeSq3 || OP == kErodeCross3 || OP == kDilateSq3 || OP == kDilateCross3) ? 4 : OP == kGauss3 ? 5 : 0;
     constexpr int kTileSmem = ROWS * kRowBytes + 16;
     constexpr int kPadded = kCtasPerSm ? (227 * 1024) / kCtasPerSm - 1024 - 512 : 0;  // 1 KiB per CTA is reserved by the driver
-    constexpr int smem_bytes = kPadded > kTileSmem ? kPadded : kTileSmem;
+    const int smem_bytes = (kPadded > kTileSmem && !g_no_occupancy_pad) ? kPadded : kTileSmem;
     const CUtensorMap* map = nullptr;
     int rc = get_tmap(ctx, const_cast<dip_image*>(src), kBoxWords, ROWS, &map);
     if (rc != DIP_OK) return rc;
