@@ -227,7 +227,7 @@ struct RowGeom {
     int valid_y0, valid_y1, out_y0, out_y1, dst_y0;
 };
 enum class Morph { Erode, Dilate };
-// `maps` (optional): per-byte maps fused into the launch; only the tiled kernels take them (stencil_tiled_op >= 0)
+// `maps` (optional): per-byte maps fused into the launch; only the 2-D tiled kernels take them (stencil_takes_maps)
 int stencil_morph(dip_ctx* ctx, Morph m, const dip_image* src, dip_image* dst, const uint8_t* mask,
                   int mw, int mh, const RowGeom& g, const ChainMaps* maps = nullptr);
 int stencil_convolve(dip_ctx* ctx, const dip_image* src, dip_image* dst, const float* k, int kw,
@@ -237,11 +237,12 @@ int stencil_convolve_sep(dip_ctx* ctx, const dip_image* src, dip_image* dst, con
 int stencil_gaussian3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps = nullptr);
 // The tiled kernel (stencil_tiled.cuh: StencilOp) that computes `op`, or -1 (direct kernel, point op, fused chain).
 int stencil_tiled_op(const dip_op& op);
+bool stencil_takes_maps(const dip_op& op);    // a two-dimensional tiled kernel: instantiated with maps (stencil_mapped.cu)
 bool stencil_is_gauss5(const dip_op& op);     // filter2D with the 5x5 Gaussian
 bool stencil_is_erode_sq3(const dip_op& op);  // 3x3 all-ones erosion (either form)
 // stencil_mapped.cu: tiled kernel `op` with the maps fused in
 int launch_tiled_mapped(dip_ctx* ctx, int op, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps& maps);
-int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g);
+int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps = nullptr);
 
 // TMA descriptor of an image view seen as a (pitch/4 words, rows, frames) u32 tensor.
 int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out);

@@ -137,7 +137,7 @@ int plan_chain(dip_ctx* ctx, const dip_op* ops, int n, int channels, std::vector
     bool gray = false, pending = false;
     auto flush_point = [&] {  // the pending segment becomes a pass of its own, or the epilogue of the previous tiled stencil
         if (!pending) return;
-        if (!gray && !plan.empty() && plan.back().kind == ChainPass::Stencil && plan.back().tiled) {
+        if (!gray && !plan.empty() && plan.back().kind != ChainPass::Point && plan.back().tiled) {
             plan.back().post = plan.back().post.then(a);
         } else if (gray || !a.identity()) {
             ChainPass p;
@@ -168,14 +168,14 @@ int plan_chain(dip_ctx* ctx, const dip_op* ops, int n, int channels, std::vector
             ChainPass p;
             p.kind = ChainPass::Stencil;
             p.op_index = i;
-            p.tiled = stencil_tiled_op(op) >= 0;
+            p.tiled = stencil_takes_maps(op);
             if (op.kind == DIP_OP_GAUSS5X5_ERODE3X3) p.kind = ChainPass::GaussErode;
             // 5x5 Gaussian directly followed by the 3x3 square erosion: the fused kernel
             const bool pair = stencil_is_gauss5(op) && i + 1 < n && stencil_is_erode_sq3(ops[i + 1]);
             if (pair) p.kind = ChainPass::GaussErode;
-            if (p.kind == ChainPass::GaussErode) p.tiled = false;  // the fused kernel takes no maps
+            if (p.kind == ChainPass::GaussErode) p.tiled = true;   // the fused kernel takes the maps like a tiled stencil
             if (pending) {
-                const bool prev_takes_it = !gray && !plan.empty() && plan.back().kind == ChainPass::Stencil && plan.back().tiled;
+                const bool prev_takes_it = !gray && !plan.empty() && plan.back().kind != ChainPass::Point && plan.back().tiled;
                 if (prev_takes_it || !p.tiled) {
                     flush_point();
                 } else if (gray) {  // (A, gray) is a pass; B rides in front of the stencil
@@ -216,7 +216,7 @@ int run_stencil_pass(dip_ctx* ctx, const dip_op& op, const ChainPass& ps, const 
     ChainMaps maps;
     maps.pre = ps.pre; maps.post = ps.post;
     const ChainMaps* mp = (ps.pre.identity() && ps.post.identity()) ? nullptr : &maps;
-    if (ps.kind == ChainPass::GaussErode) return stencil_gauss5_erode3(ctx, src, dst, g);
+    if (ps.kind == ChainPass::GaussErode) return stencil_gauss5_erode3(ctx, src, dst, g, mp);
     switch (op.kind) {
         case DIP_OP_ERODE: return stencil_morph(ctx, Morph::Erode, src, dst, op.mask, op.mask_w, op.mask_h, g, mp);
         case DIP_OP_DILATE: return stencil_morph(ctx, Morph::Dilate, src, dst, op.mask, op.mask_w, op.mask_h, g, mp);

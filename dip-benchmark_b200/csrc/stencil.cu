@@ -39,12 +39,12 @@ namespace dip {
 namespace {
 
 // Development knobs (dip_debug_set): "tile_rows" 0 = automatic, 64 or 32 forces the tile height.
-struct Knobs { int tile_rows = 0, fused_rows = 0; };
+struct Knobs { int tile_rows = 0; };
 Knobs g_knobs;
 
 // One warp band of the fused Gaussian -> erosion kernel below.  EDGE: the tile touches the image rim, so Gaussian
 // values outside the image count as 255 (+inf) for the erosion; CLIP: partial last chunk of an unpadded row.
-template <int C, int R, bool EDGE, bool CLIP, bool FULL>
+template <int C, int R, bool EDGE, bool CLIP, bool FULL, bool MAPPED, bool PRE>
 __device__ __forceinline__ void fused_band(const uint8_t* colp, const StencilParams& p, int cx, int yw, int f, int lane) {
     const int n_out = FULL ? R : min(R, p.out_y1 - yw);  // FULL: compile-time trip count (no remainder loop)
     // Gaussian bytes outside [0, rowbytes) count as 255 for the erosion: per-lane masks in packed form
@@ -67,7 +67,7 @@ __device__ __forceinline__ void fused_band(const uint8_t* colp, const StencilPar
     Acc8 m0, m1;              // horizontal minima of the two previous Gaussian rows
     Row8 row;
     auto hpass = [&](const uint8_t* rp, Acc8& h) {
-        load_row(rp, row);
+        load_row<PRE>(rp, row, &p);  // PRE: the chain's map in front of the Gaussian, applied as the words are unpacked
         hsum5<C>(row, h, 0u);
     };
     // Gaussian row g (image row yw - 1 + g) from the window, then its horizontal 3-minimum
@@ -112,7 +112,8 @@ __device__ __forceinline__ void fused_band(const uint8_t* colp, const StencilPar
 #pragma unroll
             for (int j = 0; j < 4; ++j)
                 out[j] = pack_hi(mnmx3<false>(m0.v[2 * j], m1.v[2 * j], m2.v[2 * j]), mnmx3<false>(m0.v[2 * j + 1], m1.v[2 * j + 1], m2.v[2 * j + 1]));
-            const uint4 o = make_uint4(out[0], out[1], out[2], out[3]);
+            uint4 o = make_uint4(out[0], out[1], out[2], out[3]);
+            if constexpr (MAPPED) o = map_vec(o, p.post);  // the chain's map behind the erosion
             if constexpr (CLIP) store16(dptr + (size_t)i * p.dst.pitch, o, valid);
             else __stcs(reinterpret_cast<uint4*>(dptr + (size_t)i * p.dst.pitch), o);
         }
@@ -133,7 +134,7 @@ __device__ __forceinline__ void fused_band(const uint8_t* colp, const StencilPar
 // one lane; a warp computes R+2 Gaussian rows for R output rows.  No second shared-memory tile, no
 // __syncthreads after the load.
 // =================================================================================================
-template <int C, int R, int kWarps>
+template <int C, int R, int kWarps, bool MAPPED>
 __global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
     constexpr int kThreads = kWarps * 32;
     constexpr int TO = kWarps * R;        // output rows per tile
@@ -172,14 +173,24 @@ __global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_co
     const uint8_t* colp = tile + (warp * R) * kRowBytes + kHalo + 16 * lane;  // source row yw - 3
     const bool clip = p.dst_exact && gx0 + kTileBytes > p.rowbytes && (p.rowbytes & 15) != 0;  // block-uniform, implies border
     // interior tiles (all but the image's rim) run the variant without the out-of-image masks
-    if (clip) fused_band<C, R, true, true, false>(colp, p, cx, yw, f, lane);
-    else if (border) fused_band<C, R, true, false, false>(colp, p, cx, yw, f, lane);
-    else if (yw + R <= p.out_y1) fused_band<C, R, false, false, true>(colp, p, cx, yw, f, lane);
-    else fused_band<C, R, false, false, false>(colp, p, cx, yw, f, lane);
+    if constexpr (MAPPED) {  // chains: two general variants per choice of PRE (the test stays outside the row loops)
+        if (p.has_pre) {
+            if (clip) fused_band<C, R, true, true, false, true, true>(colp, p, cx, yw, f, lane);
+            else fused_band<C, R, true, false, false, true, true>(colp, p, cx, yw, f, lane);
+        } else {
+            if (clip) fused_band<C, R, true, true, false, true, false>(colp, p, cx, yw, f, lane);
+            else fused_band<C, R, true, false, false, true, false>(colp, p, cx, yw, f, lane);
+        }
+    } else {
+        if (clip) fused_band<C, R, true, true, false, false, false>(colp, p, cx, yw, f, lane);
+        else if (border) fused_band<C, R, true, false, false, false, false>(colp, p, cx, yw, f, lane);
+        else if (yw + R <= p.out_y1) fused_band<C, R, false, false, true, false, false>(colp, p, cx, yw, f, lane);
+        else fused_band<C, R, false, false, false, false, false>(colp, p, cx, yw, f, lane);
+    }
 }
 
-template <int C, int R, int kWarps>
-int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
+template <int C, int R, int kWarps, bool MAPPED>
+int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps) {
     constexpr int TO = kWarps * R, ROWS = TO + 6;
     constexpr int smem_bytes = ROWS * kRowBytes + 16;
     const CUtensorMap* map = nullptr;
@@ -194,15 +205,20 @@ int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const 
     p.tiles_x = (src->v.rowbytes + (kTileBytes - 32) - 1) / (kTileBytes - 32);
     p.tiles_y = (g.out_y1 - g.out_y0 + TO - 1) / TO;
     p.dst_exact = exact_rows(dst->v);
+    if (MAPPED && maps) {
+        p.has_pre = !maps->pre.identity();
+        p.pre = map_params(maps->pre);
+        p.post = map_params(maps->post);
+    }
     if (p.tiles_x <= 0 || p.tiles_y <= 0) return DIP_OK;
     if (p.tiles_y > 65535 || src->v.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
     static std::atomic<uint64_t> attr_set{0};
     const uint64_t dev_bit = 1ull << (ctx->device & 63);
     if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
-        DIP_CUDA(ctx, cudaFuncSetAttribute(fused_g5e3_kernel<C, R, kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        DIP_CUDA(ctx, cudaFuncSetAttribute(fused_g5e3_kernel<C, R, kWarps, MAPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
-    DIP_CUDA(ctx, launch_kernel(fused_g5e3_kernel<C, R, kWarps>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
+    DIP_CUDA(ctx, launch_kernel(fused_g5e3_kernel<C, R, kWarps, MAPPED>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
                                 dim3(kWarps * 32), smem_bytes, ctx->compute, *map, p));
     DIP_CHECK_LAUNCH(ctx, "fused_g5e3_kernel");
     return DIP_OK;
@@ -414,6 +430,10 @@ int stencil_tiled_op(const dip_op& op) {
     return -1;
 }
 
+bool stencil_takes_maps(const dip_op& op) {
+    const int t = stencil_tiled_op(op);
+    return t >= 0 && t <= kConv5Sep;
+}
 bool stencil_is_gauss5(const dip_op& op) { return stencil_tiled_op(op) == kConv5; }
 bool stencil_is_erode_sq3(const dip_op& op) { return stencil_tiled_op(op) == kErodeSq3; }
 
@@ -477,14 +497,14 @@ int stencil_convolve_sep(dip_ctx* ctx, const dip_image* src, dip_image* dst, con
                 "run two dip_convolve passes for other kernels");
 }
 
-int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g) {
+int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps) {
     int rc = check_geom(ctx, src, dst, g);
     if (rc != DIP_OK) return rc;
-    const bool two = g_knobs.fused_rows == 2;  // development: 2-warp CTAs
+    const bool mapped = maps && !(maps->pre.identity() && maps->post.identity());
     switch (src->v.channels) {
-        case 1: return two ? launch_fused_g5e3<1, 15, 2>(ctx, src, dst, g) : launch_fused_g5e3<1, 15, 4>(ctx, src, dst, g);
-        case 3: return two ? launch_fused_g5e3<3, 15, 2>(ctx, src, dst, g) : launch_fused_g5e3<3, 15, 4>(ctx, src, dst, g);
-        case 4: return two ? launch_fused_g5e3<4, 15, 2>(ctx, src, dst, g) : launch_fused_g5e3<4, 15, 4>(ctx, src, dst, g);
+        case 1: return mapped ? launch_fused_g5e3<1, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<1, 15, 4, false>(ctx, src, dst, g, nullptr);
+        case 3: return mapped ? launch_fused_g5e3<3, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<3, 15, 4, false>(ctx, src, dst, g, nullptr);
+        case 4: return mapped ? launch_fused_g5e3<4, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<4, 15, 4, false>(ctx, src, dst, g, nullptr);
     }
     return fail(ctx, DIP_ERR_ARG, "bad channel count");
 }
@@ -504,7 +524,6 @@ extern "C" {
 int dip_debug_set(const char* key, int value) {
     if (!key) return fail(nullptr, DIP_ERR_ARG, "null key");
     if (!strcmp(key, "tile_rows")) g_knobs.tile_rows = value;
-    else if (!strcmp(key, "fused_rows")) g_knobs.fused_rows = value;
     else if (!strcmp(key, "no_pad")) g_no_occupancy_pad = value != 0;
     else return fail(nullptr, DIP_ERR_ARG, "unknown knob %s", key);
     return DIP_OK;

@@ -24,12 +24,13 @@ int launch_mapped_c(dip_ctx* ctx, const dip_image* src, dip_image* dst, const Ro
 int launch_tiled_mapped(dip_ctx* ctx, int op, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps& maps) {
     switch (op) {
 #define DIP_T(OP) case OP: return launch_mapped_c<OP>(ctx, src, dst, g, maps);
+        // the two-dimensional kernels only: the one-dimensional passes are not instantiated with maps
+        // (stencil_takes_maps; the planner gives their neighbours' maps a point pass of their own)
         DIP_T(kErodeSq3) DIP_T(kErodeCross3) DIP_T(kDilateSq3) DIP_T(kDilateCross3) DIP_T(kConv3) DIP_T(kConv3Sep) DIP_T(kGauss3)
-        DIP_T(kConv5) DIP_T(kConv5Sep) DIP_T(kErodeRow3) DIP_T(kErodeCol3) DIP_T(kDilateRow3) DIP_T(kDilateCol3) DIP_T(kConvRow3)
-        DIP_T(kConvCol3) DIP_T(kConvRow5) DIP_T(kConvCol5)
+        DIP_T(kConv5) DIP_T(kConv5Sep)
 #undef DIP_T
     }
-    return fail(ctx, DIP_ERR_ARG, "bad tiled op %d", op);
+    return fail(ctx, DIP_ERR_UNSUPPORTED, "tiled op %d takes no per-byte maps", op);
 }
 
 }  // namespace dip

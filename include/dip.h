@@ -196,7 +196,8 @@ DIP_API int dip_apply(dip_ctx* ctx, const dip_op* op, const dip_image* src, dip_
  *   - that map is fused into the neighbouring tiled stencil kernel (applied to the result, or to the source words, in
  *     registers; in front of an erosion / dilation it moves behind it, min / max commuting with monotone maps) or
  *     into the grayscale kernel, so it costs no pass of its own;
- *   - 5x5 Gaussian followed directly by 3x3 square erosion runs as the fused dip_gauss5x5_erode3x3 kernel;
+ *   - 5x5 Gaussian followed directly by 3x3 square erosion runs as the fused dip_gauss5x5_erode3x3 kernel (which takes
+ *     the maps on either side as well);
  *   - every other stencil, and every grayscale, is one pass.
  * e.g. grayscale -> GaussianBlur -> threshold -> erode: 3 passes (gray | blur+threshold | erode) instead of 4.
  * Intermediate results live in one scratch stack owned by the ctx (allocated on first use, same shape as src) and in

@@ -102,6 +102,7 @@ def test_chain_planner_counts_passes_without_a_gpu():
     assert passes(["thr", "cross", "inv"]) == 1
     assert passes(["inv", "thr", "inv", "thr"]) == 1
     assert passes(["g5", "erode"]) == 1                            # the fused Gaussian+erosion kernel
+    assert passes(["inv", "g5", "erode", "thr"]) == 1              # ... which takes the maps on both sides
     assert passes(["inv", "tall", "thr"]) == 3                     # direct kernels take no maps
     assert passes(["gray", "inv", "gray"], 3) == 1 and passes(["gray", "inv", "gray"], 4) == 2 and passes(["gray", "inv", "gray"], 1) == 1
 

@@ -18,7 +18,8 @@ ops = {"gray": mk("grayscale"), "inv": mk("invert"), "thr": mk("threshold", thre
        "erode": mk("erode", mask=np.ones((3, 3), np.uint8)), "cross": mk("erode", mask=cross),
        "g5": mk("convolve", kernel=np.outer(b5, b5)), "g5sep": mk("convolve_separable", kernel=b5, kernel_col=b5)}
 chains = [["gray", "blur", "thr", "erode"], ["thr", "cross", "inv"], ["inv", "thr", "inv"], ["thr", "g5sep", "inv"], ["g5", "erode", "thr"],
-          ["gray", "thr"], ["inv", "g5sep"]]
+          ["gray", "thr"], ["inv", "g5sep"], ["g5", "erode"], ["g5", "erode", "inv"], ["inv", "g5", "erode"],
+          ["g5sep"], ["g5sep", "inv"], ["g5sep", "thr"], ["blur"], ["blur", "thr"], ["thr", "blur"]]
 print("| chain | passes | chain us/frame | one by one us/frame | ratio |")
 print("|---|---|---|---|---|")
 for names in chains:
