@@ -103,7 +103,9 @@ DIP_API int dip_host_unregister(void* ptr);
 /* ---- memory operations -------------------------------------------------------- */
 /* "Upload": cv.UMat(cpu_image) opencv:92, q.memcpy(d_input, image.data) sycl:331,
  * vglClUpload vgl:119.  host = frames x H rows of W*C bytes, rows host_pitch apart
- * (0 = tightly packed), frames host_pitch*H apart. */
+ * (0 = tightly packed), frames host_pitch*H apart.  Pinned host memory (dip_host_alloc / dip_host_register) is one
+ * asynchronous copy at the PCIe rate (55-57 GB/s); pageable memory goes through two 8 MiB pinned staging slots filled by
+ * a small pool of host threads (38-44 GB/s; env DIP_COPY_THREADS / DIP_COPY_SPIN_US tune the pool). */
 DIP_API int dip_upload(dip_ctx* ctx, dip_image* dst, const uint8_t* host, size_t host_pitch);
 /* "Download": image.get() opencv:93, sycl:332, vglClDownload vgl:120 */
 DIP_API int dip_download(dip_ctx* ctx, const dip_image* src, uint8_t* host, size_t host_pitch);
