@@ -12,12 +12,33 @@ rng = np.random.default_rng(seed)
 ctx = dip.Context(0)
 fused = lambda im: orc.erode(orc.filter2d(im, orc.BLUR_5X5), orc.SQUARE_MASK)  # noqa: E731
 OPS = list(zip(dip.REFERENCE_OPS, [f for _, f in orc.OPERATIONS])) + [(("fused", "gauss5x5_erode3x3", ()), fused)]
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from test_parity_gpu import _chain_pool  # the op pool of the chain tests: name -> (dip_op, oracle function)
+POOL = _chain_pool(dip, orc)
+POOL_NAMES = sorted(POOL)
 t0 = time.time()
 fails = 0
 for t in range(trials):
-    kind = rng.integers(0, 10)
+    kind = rng.integers(0, 13)
     c = int(rng.choice([1, 3, 4]))
-    if kind < 6:      # plain op on a random stack
+    if kind >= 10:    # op chain (dip_apply_chain) against the ops applied one by one by the oracle
+        h = int(rng.integers(1, 200)); w = int(rng.integers(1, 1100)); n = int(rng.choice([1, 1, 2]))
+        img = rng.integers(0, 256, (n, h, w, c), dtype=np.uint8)
+        if rng.random() < 0.3:
+            img = (img // 32 * 36).astype(np.uint8)
+        names = [POOL_NAMES[int(i)] for i in rng.integers(0, len(POOL_NAMES), int(rng.integers(1, 8)))]
+        src = ctx.from_array(img); dst = ctx.image_like(src)
+        ctx.apply_chain([POOL[nm][0] for nm in names], src, dst)
+        got = dst.download().reshape(img.shape)
+        ok = True
+        for f in range(n):
+            want = img[f]
+            for nm in names:
+                want = POOL[nm][1](want)
+            ok = ok and np.array_equal(got[f], want)
+        desc = f"chain {names} on {n}x{h}x{w}x{c}"
+        src.close(); dst.close()
+    elif kind < 6:      # plain op on a random stack
         h = int(rng.integers(1, 260)); w = int(rng.integers(1, 1300)); n = int(rng.choice([1, 1, 1, 2, 5]))
         img = rng.integers(0, 256, (n, h, w, c), dtype=np.uint8)
         if rng.random() < 0.3:
