@@ -1,7 +1,7 @@
 """Parity of the 12 reference ops against the oracle with development knobs set.
-usage: python tools/check_knob.py knob=value[,knob=value]"""
+usage: python tests/soak/check_knob.py knob=value[,knob=value]"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np
 from _dip_pkg import load
 from oracle import oracle as orc

@@ -1,8 +1,8 @@
 """Randomised parity soak against the CPU oracle (test infrastructure; not part of the product path).
-usage: python tools/stress.py [trials=400] [seed=1]"""
+usage: python tests/soak/stress.py [trials=400] [seed=1]"""
 import os, sys, time
 import numpy as np
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from _dip_pkg import load
 from oracle import oracle as orc
 dip = load()
@@ -12,7 +12,7 @@ rng = np.random.default_rng(seed)
 ctx = dip.Context(0)
 fused = lambda im: orc.erode(orc.filter2d(im, orc.BLUR_5X5), orc.SQUARE_MASK)  # noqa: E731
 OPS = list(zip(dip.REFERENCE_OPS, [f for _, f in orc.OPERATIONS])) + [(("fused", "gauss5x5_erode3x3", ()), fused)]
-sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from test_parity_gpu import _chain_pool  # the op pool of the chain tests: name -> (dip_op, oracle function)
 POOL = _chain_pool(dip, orc)
 POOL_NAMES = sorted(POOL)
