@@ -140,3 +140,25 @@ def test_byte_wise_runs_fold_into_one_exact_map():
                 run([("inv", 0, 0), ("thr", t1, m1), ("thr", t2, 77)])
     with pytest.raises(DipError):
         Context.chain_lut([make_op("grayscale")])
+
+
+def _build_c_example(tmp_path):
+    import subprocess
+    lib_dir = os.path.join(ROOT, "dip-benchmark_b200")
+    exe = str(tmp_path / "chain")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "examples", "chain.c"), "-L", lib_dir, "-ldip_b200", "-Wl,-rpath," + lib_dir, "-o", exe])
+    return exe
+
+
+def test_plain_c_caller_links_and_fails_loudly_without_a_gpu(dip, tmp_path):
+    """examples/chain.c (C99, no C++ runtime on the caller's side) links against the C-ABI; on a box without a GPU
+    dip_init reports DIP_ERR_NO_DEVICE and the program exits 4 -- there is no CPU fallback to fall into."""
+    import ctypes as C
+    import subprocess
+    exe = _build_c_example(tmp_path)
+    n = C.c_int(0)
+    if dip.lib().dip_device_count(C.byref(n)) == 0 and n.value > 0:
+        pytest.skip("a GPU is present: covered by the gpu test")
+    r = subprocess.run([exe, "64", "48", str(tmp_path / "out.raw")], capture_output=True, text=True)
+    assert r.returncode == 4 and "no GPU" in r.stderr, (r.returncode, r.stderr)

@@ -724,3 +724,20 @@ def test_chain_errors(ctx, dip, orc):
     with pytest.raises(dip.DipError):
         ctx.apply_chain([bad], img, other)
     img.close(); other.close()
+
+
+def test_plain_c_example_chain(ctx, dip, orc, tmp_path):
+    """examples/chain.c: grayscale -> GaussianBlur -> threshold -> erosion through dip_apply_chain from a C99 program."""
+    import subprocess
+    from test_abi import _build_c_example
+    exe = _build_c_example(tmp_path)
+    w, h = 333, 97
+    out = tmp_path / "out.raw"
+    r = subprocess.run([exe, str(w), str(h), str(out)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert "4 operations in 3 passes" in r.stdout
+    i = np.arange(w * h * 3, dtype=np.uint64)
+    img = (((i * 2654435761) & 0xFFFFFFFF) >> 13).astype(np.uint8).reshape(h, w, 3)   # the example's content (32-bit product)
+    want = orc.erode(orc.threshold(orc.gaussian_blur3x3(orc.grayscale(img)), 127, 255), orc.SQUARE_MASK)
+    got = np.frombuffer(out.read_bytes(), np.uint8).reshape(h, w, 3)
+    assert np.array_equal(got, want)
