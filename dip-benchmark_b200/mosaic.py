@@ -19,22 +19,29 @@ from . import shard
 
 
 class MosaicBand:
-    def __init__(self, ctx, width: int, total_rows: int, world: int, rank: int, radii=(2, 1), fused: bool = False):
-        """fused=True runs the chain as ONE kernel (dip_gauss5x5_erode3x3, halo 3): half the HBM traffic."""
+    def __init__(self, ctx, width: int, total_rows: int, world: int, rank: int, radii=(2, 1), fused: bool = False,
+                 chain=None, channels: int = 1):
+        """fused=True runs the default chain as ONE kernel (dip_gauss5x5_erode3x3, halo 3): half the HBM traffic.
+        chain=[(dip_op, vertical radius), ...] runs any sequence of operations instead (radius 0 for point ops, 1 for the
+        3-tap stencils, 2 for the 5-tap ones): one halo exchange of sum(radii) rows per step, overlap recomputed."""
         self.ctx = ctx
         self.width, self.total_rows, self.world, self.rank = width, total_rows, world, rank
         self.fused = fused
-        self.radii = [3] if fused else list(radii)
+        self.radii = [r for _, r in chain] if chain is not None else [3] if fused else list(radii)
         self.halo = shard.chain_halo(self.radii)
         self.band = shard.mosaic_band(total_rows, world, rank, self.halo)
         b = self.band
-        self.bufs = [ctx.image(width, b.buffer_rows, 1) for _ in range(len(self.radii) + 1)]
+        self.channels = channels
+        self.bufs = [ctx.image(width, b.buffer_rows, channels) for _ in range(len(self.radii) + 1)]
         self.plan = shard.chain_row_plan(b, self.radii)
         self.above = None   # neighbours' input band buffers
         self.below = None
         self._imported = []  # IPC-mapped images this band opened (closed with it)
         ops = {p: op for _, p, op in ctx.reference_ops()}
-        self.chain = [ctx.fused_chain_op()] if fused else [ops["convolution-gaussian-blur-5x5"], ops["erosion-square"]][: len(self.radii)]
+        if chain is not None:
+            self.chain = [op for op, _ in chain]
+        else:
+            self.chain = [ctx.fused_chain_op()] if fused else [ops["convolution-gaussian-blur-5x5"], ops["erosion-square"]][: len(self.radii)]
 
     # -- setup ---------------------------------------------------------------------------------
     def fill_synthetic(self, seed: int = 0):
@@ -49,11 +56,11 @@ class MosaicBand:
         """handles[r] = export_handle() of rank r (gathered by the caller, e.g. all_gather_object)."""
         if self.band.has_above:
             h = handles[self.rank - 1]
-            self.above = (self.ctx.ipc_import(h["handle"], self.width, h["buffer_rows"]), h)
+            self.above = (self.ctx.ipc_import(h["handle"], self.width, h["buffer_rows"], self.channels), h)
             self._imported.append(self.above[0])
         if self.band.has_below:
             h = handles[self.rank + 1]
-            self.below = (self.ctx.ipc_import(h["handle"], self.width, h["buffer_rows"]), h)
+            self.below = (self.ctx.ipc_import(h["handle"], self.width, h["buffer_rows"], self.channels), h)
             self._imported.append(self.below[0])
 
     def connect_local(self, bands: list["MosaicBand"]):
@@ -69,6 +76,8 @@ class MosaicBand:
     def exchange(self):
         """Pull halo rows from the neighbours (halo stream; returns immediately)."""
         b = self.band
+        if self.halo == 0:   # a chain of point operations needs no neighbour rows
+            return
         if self.above is not None:
             img, h = self.above
             self.bufs[0].copy_rows_from(img, h["own0"] + h["rows"] - self.halo, b.recv_above_row(), self.halo)
@@ -77,7 +86,7 @@ class MosaicBand:
             self.bufs[0].copy_rows_from(img, h["own0"], b.recv_below_row(), self.halo)
 
     def halo_bytes(self) -> int:
-        return self.halo * self.width * (int(self.band.has_above) + int(self.band.has_below))
+        return self.halo * self.width * self.channels * (int(self.band.has_above) + int(self.band.has_below))
 
     def step(self, overlap: bool = True):
         ctx, b = self.ctx, self.band

@@ -741,3 +741,32 @@ def test_plain_c_example_chain(ctx, dip, orc, tmp_path):
     want = orc.erode(orc.threshold(orc.gaussian_blur3x3(orc.grayscale(img)), 127, 255), orc.SQUARE_MASK)
     got = np.frombuffer(out.read_bytes(), np.uint8).reshape(h, w, 3)
     assert np.array_equal(got, want)
+
+
+def test_mosaic_bands_run_any_chain(ctx, dip, orc):
+    """Row bands with one halo exchange per step for arbitrary op sequences (point ops radius 0, 3-tap 1, 5-tap 2),
+    1 and 3 channels: the concatenated bands equal the whole-image oracle."""
+    pool = _chain_pool(dip, orc)
+    radius = {"invert": 0, "thr60": 0, "gray": 0, "erode_cross": 1, "dilate_sq": 1, "gauss3": 1, "conv3sep": 1, "conv5": 2, "conv5sep": 2, "erode_tall": 2}
+    rng = np.random.default_rng(31)
+    for names, c in [(["gauss3", "thr60", "erode_cross", "conv5sep"], 1), (["gray", "conv5", "invert", "dilate_sq"], 3),
+                     (["erode_tall", "conv3sep"], 1), (["invert"], 3)]:
+        width, rows = 700, 333
+        whole = rand_img(rng, rows, width, c)
+        want = whole
+        for n in names:
+            want = pool[n][1](want)
+        chain = [(pool[n][0], radius[n]) for n in names]
+        for world in (1, 2, 4):
+            bands = [dip.mosaic.MosaicBand(ctx, width, rows, world, r, chain=chain, channels=c) for r in range(world)]
+            for b in bands:
+                b.bufs[0].rows(b.band.own0, b.band.rows).upload(whole[b.band.row0: b.band.row0 + b.band.rows])
+            ctx.sync()
+            for b in bands:
+                b.connect_local(bands)
+            for b in bands:
+                b.step(overlap=True)
+            out = np.concatenate([b.result().download().reshape(-1, width, c) for b in bands], axis=0)
+            assert np.array_equal(out, want), (names, c, world)
+            for b in bands:
+                b.close()
