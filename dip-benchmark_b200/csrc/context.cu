@@ -17,6 +17,7 @@
 #include <mutex>
 #include <thread>
 
+#include "copy_pool.h"
 #include "dip_internal.h"
 
 namespace dip {
@@ -405,82 +406,6 @@ int dip_host_unregister(void* p) {
 // created on first use (a transfer is a train of 8 MiB slices; creating threads per slice cost as much as a third of the
 // copy); they spin for the next slice for 0.5 ms (waking sleepers one by one is what made single-frame calls slow), then
 // sleep.  DIP_COPY_THREADS / DIP_COPY_SPIN_US override the pool width (default min(12, 3/4 of the cores)) and the spin time.
-namespace {
-
-class CopyPool {
-public:
-    static CopyPool& get() {
-        static CopyPool* pool = new CopyPool();  // leaked on purpose: the workers outlive every ctx and are never joined
-        return *pool;
-    }
-    unsigned width() const { return (unsigned)workers_ + 1; }
-    // run f(0 .. n-1) on the pool; the caller takes part and returns when all n are done
-    void run(unsigned n, const std::function<void(unsigned)>& f) {
-        if (n <= 1) { f(0); return; }
-        std::lock_guard<std::mutex> serial(run_mutex_);  // one transfer at a time uses the pool
-        job_ = &f;
-        limit_.store(n, std::memory_order_relaxed);
-        pending_.store((int)n, std::memory_order_relaxed);
-        const uint64_t gen = (state_.load(std::memory_order_relaxed) >> 32) + 1;
-        {
-            std::lock_guard<std::mutex> lk(m_);
-            state_.store(gen << 32, std::memory_order_release);  // publishes job_, limit_, pending_
-        }
-        cv_.notify_all();
-        work(gen);
-        while (pending_.load(std::memory_order_acquire) > 0) std::this_thread::yield();
-    }
-
-private:
-    CopyPool() {
-        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-        workers_ = (int)std::min(12u, std::max(1u, hw * 3 / 4)) - 1;
-        if (const char* e = getenv("DIP_COPY_THREADS")) workers_ = std::max(0, std::min(63, atoi(e) - 1));
-        if (const char* e = getenv("DIP_COPY_SPIN_US")) spin_us_ = std::max(0, atoi(e));
-        for (int i = 0; i < workers_; ++i) std::thread([this] { loop(); }).detach();
-    }
-    // Claim task indices of generation `gen` one at a time.  Generation and next index share one atomic word, so a
-    // worker that is late for an old generation can never claim (or read the job of) a newer one by accident.
-    void work(uint64_t gen) {
-        for (;;) {
-            uint64_t s = state_.load(std::memory_order_acquire);
-            if ((s >> 32) != gen) return;
-            const unsigned t = (unsigned)(s & 0xFFFFFFFFu);
-            if (t >= limit_.load(std::memory_order_relaxed)) return;
-            if (state_.compare_exchange_weak(s, s + 1, std::memory_order_acq_rel)) {
-                (*job_)(t);
-                pending_.fetch_sub(1, std::memory_order_release);
-            }
-        }
-    }
-    void loop() {
-        uint64_t seen = 0;
-        for (;;) {
-            // spin for the next slice of the same transfer, then sleep
-            const auto t0 = std::chrono::steady_clock::now();
-            while ((state_.load(std::memory_order_acquire) >> 32) == seen) {
-                if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us_)) {
-                    std::unique_lock<std::mutex> lk(m_);
-                    cv_.wait(lk, [&] { return (state_.load(std::memory_order_acquire) >> 32) != seen; });
-                    break;
-                }
-            }
-            seen = state_.load(std::memory_order_acquire) >> 32;
-            work(seen);
-        }
-    }
-    int workers_ = 0;
-    int spin_us_ = 500;  // measured on a 16-core host: one 24.5 MB frame per call moves at 17 GB/s with 50 us, 38 GB/s with 500 us
-    std::mutex m_, run_mutex_;
-    std::condition_variable cv_;
-    std::atomic<uint64_t> state_{0};  // generation << 32 | next task index
-    std::atomic<unsigned> limit_{0};
-    std::atomic<int> pending_{0};
-    const std::function<void(unsigned)>* job_ = nullptr;
-};
-
-}  // namespace
-
 static void host_copy_rows(uint8_t* dst, size_t dpitch, const uint8_t* src, size_t spitch, size_t rowbytes, int rows) {
     const size_t total = rowbytes * (size_t)rows;
     if (total < ((size_t)1 << 20)) {  // small: not worth waking anybody
@@ -488,7 +413,7 @@ static void host_copy_rows(uint8_t* dst, size_t dpitch, const uint8_t* src, size
         else for (int r = 0; r < rows; ++r) memcpy(dst + dpitch * r, src + spitch * r, rowbytes);
         return;
     }
-    CopyPool& pool = CopyPool::get();
+    dip::CopyPool& pool = dip::CopyPool::get();
     const unsigned nthreads = (unsigned)std::min<size_t>(pool.width(), total >> 19);  // at least 512 KiB per thread
     pool.run(nthreads, [=](unsigned t) {
         if (dpitch == rowbytes && spitch == rowbytes) {

@@ -162,3 +162,14 @@ def test_plain_c_caller_links_and_fails_loudly_without_a_gpu(dip, tmp_path):
         pytest.skip("a GPU is present: covered by the gpu test")
     r = subprocess.run([exe, "64", "48", str(tmp_path / "out.raw")], capture_output=True, text=True)
     assert r.returncode == 4 and "no GPU" in r.stderr, (r.returncode, r.stderr)
+
+
+def test_staging_copy_pool_runs_every_task_exactly_once(tmp_path):
+    """csrc/copy_pool.h (the host threads behind pageable uploads / downloads): 240 000 runs from four caller threads
+    with varying task counts, default spin and a spin so short that workers keep falling asleep."""
+    exe = str(tmp_path / "copy_pool_stress")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "dip-benchmark_b200", "csrc"),
+                           os.path.join(ROOT, "tests", "copy_pool_stress.cpp"), "-o", exe])
+    for env in ({}, {"DIP_COPY_THREADS": "5", "DIP_COPY_SPIN_US": "5"}):
+        r = subprocess.run([exe], capture_output=True, text=True, env={**os.environ, **env}, timeout=300)
+        assert r.returncode == 0 and "errors 0" in r.stdout, (env, r.stdout, r.stderr)
