@@ -116,6 +116,8 @@ def lib() -> C.CDLL:
         "dip_reference_op_description": ([i], C.c_char_p),
         "dip_run_ops_host": ([vp, vp, i, i, i, i, P(Op), i, P(vp), i], i),
         "dip_pipeline_create": ([vp, i, i, i, i, P(Op), i, P(vp)], i),
+        "dip_pipeline_create_chain": ([vp, i, i, i, i, P(Op), i, P(vp)], i),
+        "dip_run_chain_host": ([vp, vp, i, i, i, i, P(Op), i, vp, i], i),
         "dip_pipeline_run": ([vp, vp, i, i, P(vp), i], i),
         "dip_pipeline_destroy": ([vp], i),
         "dip_mark": ([vp, i], i),

@@ -16,6 +16,8 @@ using namespace dip;
 struct dip_pipeline {
     dip_ctx* ctx = nullptr;
     int w = 0, h = 0, c = 0, chunk = 0, n_ops = 0;
+    bool chain = false;                       // ops applied in sequence, one output (dip_pipeline_create_chain)
+    int n_out = 0;                            // outputs per chunk: n_ops, or 1 for a chain
     std::vector<dip_op> ops;
     dip_image* in[2] = {nullptr, nullptr};
     std::vector<dip_image*> out;              // [slot][op]
@@ -334,30 +336,56 @@ extern "C" int dip_apply_rows(dip_ctx* ctx, const dip_op* op, const dip_image* s
 
 extern "C" {
 
-int dip_pipeline_create(dip_ctx* ctx, int w, int h, int c, int chunk_frames, const dip_op* ops, int n_ops, dip_pipeline** out) {
+static int pipeline_create(dip_ctx* ctx, int w, int h, int c, int chunk_frames, const dip_op* ops, int n_ops, bool chain, dip_pipeline** out) {
     if (!ctx || !ops || !out || n_ops < 1 || chunk_frames < 1) return fail(ctx, DIP_ERR_ARG, "bad argument");
     *out = nullptr;
     dip_pipeline* p = new (std::nothrow) dip_pipeline();
     if (!p) return fail(ctx, DIP_ERR_NOMEM, "out of host memory");
     p->ctx = ctx; p->w = w; p->h = h; p->c = c; p->chunk = chunk_frames; p->n_ops = n_ops;
+    p->chain = chain;
+    p->n_out = chain ? 1 : n_ops;
     p->ops.assign(ops, ops + n_ops);
-    p->out.assign(2 * (size_t)n_ops, nullptr);
-    p->out_ready.assign(2 * (size_t)n_ops, nullptr);
-    p->out_free.assign(2 * (size_t)n_ops, nullptr);
+    const int n_out = p->n_out;
+    p->out.assign(2 * (size_t)n_out, nullptr);
+    p->out_ready.assign(2 * (size_t)n_out, nullptr);
+    p->out_free.assign(2 * (size_t)n_out, nullptr);
     int rc = DIP_OK;
     cudaSetDevice(ctx->device);
     auto mk = [&](cudaEvent_t* e) { if (rc == DIP_OK && cudaEventCreateWithFlags(e, cudaEventDisableTiming) != cudaSuccess) rc = fail(ctx, DIP_ERR_CUDA, "cudaEventCreate failed"); };
     for (int s = 0; s < 2 && rc == DIP_OK; ++s) {
         rc = dip_image_create_batch(ctx, w, h, c, chunk_frames, &p->in[s]);
         mk(&p->in_ready[s]); mk(&p->in_free[s]);
-        for (int o = 0; o < n_ops && rc == DIP_OK; ++o) {
-            rc = dip_image_create_batch(ctx, w, h, c, chunk_frames, &p->out[(size_t)s * n_ops + o]);
-            mk(&p->out_ready[(size_t)s * n_ops + o]); mk(&p->out_free[(size_t)s * n_ops + o]);
+        for (int o = 0; o < n_out && rc == DIP_OK; ++o) {
+            rc = dip_image_create_batch(ctx, w, h, c, chunk_frames, &p->out[(size_t)s * n_out + o]);
+            mk(&p->out_ready[(size_t)s * n_out + o]); mk(&p->out_free[(size_t)s * n_out + o]);
         }
     }
     if (rc != DIP_OK) { dip_pipeline_destroy(p); return rc; }
     *out = p;
     return DIP_OK;
+}
+
+int dip_pipeline_create(dip_ctx* ctx, int w, int h, int c, int chunk_frames, const dip_op* ops, int n_ops, dip_pipeline** out) {
+    return pipeline_create(ctx, w, h, c, chunk_frames, ops, n_ops, false, out);
+}
+
+int dip_pipeline_create_chain(dip_ctx* ctx, int w, int h, int c, int chunk_frames, const dip_op* ops, int n_ops, dip_pipeline** out) {
+    return pipeline_create(ctx, w, h, c, chunk_frames, ops, n_ops, true, out);
+}
+
+int dip_run_chain_host(dip_ctx* ctx, const uint8_t* host_in, int w, int h, int c, int frames, const dip_op* ops, int n_ops,
+                       uint8_t* host_out, int chunk_frames) {
+    if (!ctx || !host_in || !ops || !host_out || n_ops < 1 || frames < 1) return fail(ctx, DIP_ERR_ARG, "bad argument");
+    if (chunk_frames < 1) chunk_frames = 4;
+    chunk_frames = std::min(chunk_frames, frames);
+    dip_pipeline* p = nullptr;
+    int rc = dip_pipeline_create_chain(ctx, w, h, c, chunk_frames, ops, n_ops, &p);
+    if (rc != DIP_OK) return rc;
+    const int ring = (frames + chunk_frames - 1) / chunk_frames * chunk_frames;
+    uint8_t* outs[1] = {host_out};
+    rc = dip_pipeline_run(p, host_in, ring, frames, outs, ring);
+    dip_pipeline_destroy(p);
+    return rc;
 }
 
 int dip_pipeline_destroy(dip_pipeline* p) {
@@ -396,13 +424,13 @@ int dip_pipeline_run(dip_pipeline* p, const uint8_t* host_in, int in_ring, int f
             DIP_CUDA(ctx, cudaEventRecord(p->in_ready[slot], ctx->upload));
             DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, p->in_ready[slot], 0));
         }
-        for (int o = 0; o < p->n_ops && rc == DIP_OK; ++o) {
-            const size_t idx = (size_t)slot * p->n_ops + o;
+        for (int o = 0; o < p->n_out && rc == DIP_OK; ++o) {
+            const size_t idx = (size_t)slot * p->n_out + o;
             dip_image* ov = nullptr;
             if ((rc = dip_image_view(ctx, p->out[idx], 0, n, &ov)) != DIP_OK) break;
             // the kernel may overwrite this output slot only after its previous download finished
             if (used[slot]) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, p->out_free[idx], 0));
-            rc = dip_apply(ctx, &p->ops[o], iv, ov);
+            rc = p->chain ? dip_apply_chain(ctx, p->ops.data(), p->n_ops, iv, ov) : dip_apply(ctx, &p->ops[o], iv, ov);
             if (rc == DIP_OK) {
                 DIP_CUDA(ctx, cudaEventRecord(p->out_ready[idx], ctx->compute));
                 DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->download, p->out_ready[idx], 0));

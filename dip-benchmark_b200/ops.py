@@ -280,8 +280,17 @@ class Context:
         outs = (C.c_void_p * len(ops))(*[o.ctypes.data for o in host_out])
         check(lib().dip_run_ops_host(self._h, a.ctypes.data, w, hgt, c, n, arr, len(ops), outs, chunk_frames), self._h)
 
-    def pipeline(self, width: int, height: int, channels: int, chunk_frames: int, ops) -> "Pipeline":
-        return Pipeline(self, width, height, channels, chunk_frames, ops)
+    def run_chain_host(self, host_in: np.ndarray, ops, host_out: np.ndarray, chunk_frames: int = 4):
+        """Upload -> the ops in sequence (dip_apply_chain) -> download the final result only (dip_run_chain_host)."""
+        a = host_in
+        assert a.dtype == np.uint8 and a.flags.c_contiguous and a.ndim == 4
+        assert host_out.dtype == np.uint8 and host_out.flags.c_contiguous and host_out.shape == a.shape
+        n, hgt, w, c = a.shape
+        arr = (capi.Op * len(ops))(*ops)
+        check(lib().dip_run_chain_host(self._h, a.ctypes.data, w, hgt, c, n, arr, len(ops), host_out.ctypes.data, chunk_frames), self._h)
+
+    def pipeline(self, width: int, height: int, channels: int, chunk_frames: int, ops, chain: bool = False) -> "Pipeline":
+        return Pipeline(self, width, height, channels, chunk_frames, ops, chain=chain)
 
     # -- timing ---------------------------------------------------------------------------------
     def mark(self, slot: int):
@@ -322,17 +331,22 @@ class Context:
 class Pipeline:
     """Persistent upload -> ops -> download pipeline over host rings (dip_pipeline_*)."""
 
-    def __init__(self, ctx: Context, width: int, height: int, channels: int, chunk_frames: int, ops):
+    def __init__(self, ctx: Context, width: int, height: int, channels: int, chunk_frames: int, ops, chain: bool = False):
+        """chain=True: the ops run in sequence and only the final result is downloaded (host_out has one entry)."""
         self.ctx = ctx
+        self._keep = list(ops)
         self._ops = (capi.Op * len(ops))(*ops)
         self.n_ops = len(ops)
+        self.n_out = 1 if chain else len(ops)
         self.chunk = chunk_frames
         self._h = C.c_void_p()
-        check(lib().dip_pipeline_create(ctx._h, width, height, channels, chunk_frames, self._ops, len(ops), C.byref(self._h)), ctx._h)
+        create = lib().dip_pipeline_create_chain if chain else lib().dip_pipeline_create
+        check(create(ctx._h, width, height, channels, chunk_frames, self._ops, len(ops), C.byref(self._h)), ctx._h)
 
     def run(self, host_in: np.ndarray, frames: int, host_out: list[np.ndarray]):
         """host_in: (in_ring, H, W, C); host_out[i]: (out_ring, H, W, C); rings are multiples of chunk."""
-        outs = (C.c_void_p * self.n_ops)(*[o.ctypes.data for o in host_out])
+        assert len(host_out) == self.n_out
+        outs = (C.c_void_p * self.n_out)(*[o.ctypes.data for o in host_out])
         check(lib().dip_pipeline_run(self._h, host_in.ctypes.data, host_in.shape[0], frames, outs, host_out[0].shape[0]), self.ctx._h)
 
     def close(self):

@@ -240,6 +240,12 @@ DIP_API int dip_pipeline_create(dip_ctx* ctx, int width, int height, int channel
 DIP_API int dip_pipeline_run(dip_pipeline* pipe, const uint8_t* host_in, int in_ring_frames, int frames,
                              uint8_t* const* host_out, int out_ring_frames);
 DIP_API int dip_pipeline_destroy(dip_pipeline* pipe);
+/* Chain form: the ops are applied IN SEQUENCE (dip_apply_chain) and only the final result comes back, so a frame
+ * crosses PCIe once in each direction: host_out[0] receives the `frames` results.  Same rings, same overlap. */
+DIP_API int dip_pipeline_create_chain(dip_ctx* ctx, int width, int height, int channels, int chunk_frames,
+                                      const dip_op* ops, int n_ops, dip_pipeline** pipe);
+DIP_API int dip_run_chain_host(dip_ctx* ctx, const uint8_t* host_in, int width, int height, int channels, int frames,
+                               const dip_op* ops, int n_ops, uint8_t* host_out, int chunk_frames);
 
 /* ---- device-side timing on the ctx's compute stream (measure_time opencv:26-38,
  *      sycl:25-39 use a host clock; these are CUDA events) --------------------------- */

@@ -770,3 +770,26 @@ def test_mosaic_bands_run_any_chain(ctx, dip, orc):
             assert np.array_equal(out, want), (names, c, world)
             for b in bands:
                 b.close()
+
+
+def test_chain_host_pipeline(ctx, dip, orc):
+    """dip_run_chain_host: frames cross PCIe once each way, the ops run in sequence on the device (pageable and pinned
+    host buffers, a last chunk that is not full)."""
+    pool = _chain_pool(dip, orc)
+    rng = np.random.default_rng(91)
+    names = ["gray", "gauss3", "thr", "erode_sq", "invert"]
+    stack = np.stack([rand_img(rng, 90, 260, 3) for _ in range(7)])
+    want = stack.copy()
+    for f in range(len(stack)):
+        im = stack[f]
+        for n in names:
+            im = pool[n][1](im)
+        want[f] = im
+    ops = [pool[n][0] for n in names]
+    out = np.zeros_like(stack)
+    ctx.run_chain_host(stack, ops, out, chunk_frames=3)          # pageable buffers, chunks of 3 + 3 + 1
+    assert np.array_equal(out, want)
+    pin_in = ctx.pinned_empty(stack.shape); pin_in[...] = stack
+    pin_out = ctx.pinned_empty(stack.shape); pin_out[...] = 0
+    ctx.run_chain_host(pin_in, ops, pin_out, chunk_frames=2)
+    assert np.array_equal(pin_out, want)
