@@ -197,7 +197,8 @@ DIP_API int dip_apply(dip_ctx* ctx, const dip_op* op, const dip_image* src, dip_
  *   - runs of byte-wise ops (copy, inversion, threshold) collapse into ONE per-byte map (identity, 255 - x or a step);
  *   - that map is fused into the neighbouring tiled stencil kernel (applied to the result, or to the source words, in
  *     registers; in front of an erosion / dilation it moves behind it, min / max commuting with monotone maps) or
- *     into the grayscale kernel, so it costs no pass of its own;
+ *     into the grayscale kernel, so it costs no pass of its own (next to a direct kernel for an arbitrary mask, or
+ *     a one-dimensional pass, it becomes one point pass instead);
  *   - 5x5 Gaussian followed directly by 3x3 square erosion runs as the fused dip_gauss5x5_erode3x3 kernel (which takes
  *     the maps on either side as well);
  *   - every other stencil, and every grayscale, is one pass.
