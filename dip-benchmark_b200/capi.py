@@ -8,7 +8,8 @@ import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-_LIB = os.path.join(_HERE, "libdip_b200.so")
+# DIP_B200_LIB: another build of the same library (compile-time variants for A/B measurements, tools/README.md)
+_LIB = os.environ.get("DIP_B200_LIB") or os.path.join(_HERE, "libdip_b200.so")
 _HEADER = os.path.join(_ROOT, "include", "dip.h")
 _lib = None
 

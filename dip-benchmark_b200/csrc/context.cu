@@ -71,12 +71,12 @@ static int new_image(dip_ctx* ctx, dip_image** out) {
     if (!im) return fail(ctx, DIP_ERR_NOMEM, "out of host memory");
     im->ctx = ctx;
     im->device = ctx ? ctx->device : -1;
-    cudaError_t e = cudaEventCreateWithFlags(&im->copy_done, cudaEventDisableTiming);
-    if (e != cudaSuccess) {
-        delete im;
-        return fail_cuda(ctx, e, "cudaEventCreate", __FILE__, __LINE__);
-    }
-    *out = im;
+    *out = im;  // copy_done is created by the first transfer that needs it (views never do: copies are tracked on the root)
+    return DIP_OK;
+}
+
+static int ensure_copy_event(dip_ctx* ctx, dip_image* im) {
+    if (!im->copy_done) DIP_CUDA(ctx, cudaEventCreateWithFlags(&im->copy_done, cudaEventDisableTiming));
     return DIP_OK;
 }
 
@@ -101,17 +101,21 @@ static PFN_encodeTiled encode_tiled_fn() {
 }
 
 int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out) {
-    for (const TmapKey& k : img->tmaps)
-        if (k.box_words == box_words && k.box_rows == box_rows) {
+    const ImgView& v = img->v;
+    dip_image* root = root_of(img);
+    for (const TmapKey& k : root->tmaps)
+        if (k.base == v.base && k.pitch == v.pitch && k.frame_stride == v.frame_stride && k.rowbytes == v.rowbytes &&
+            k.height == v.height && k.frames == v.frames && k.box_words == box_words && k.box_rows == box_rows) {
             *out = &k.map;
             return DIP_OK;
         }
     PFN_encodeTiled enc = encode_tiled_fn();
     if (!enc) return fail(ctx, DIP_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-    const ImgView& v = img->v;
     if ((reinterpret_cast<uintptr_t>(v.base) & 15) || (v.pitch & 15) || (v.frame_stride & 15))
         return fail(ctx, DIP_ERR_ARG, "image base/pitch/frame stride must be 16-byte aligned for TMA");
     TmapKey key{};
+    key.base = v.base; key.pitch = v.pitch; key.frame_stride = v.frame_stride;
+    key.rowbytes = v.rowbytes; key.height = v.height; key.frames = v.frames;
     key.box_words = box_words;
     key.box_rows = box_rows;
     // (x in 4-byte words, y, frame): u32 elements lift the 256-element box limit to 1 KiB rows.  The x extent is
@@ -129,8 +133,9 @@ int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CU
     if (r != CUDA_SUCCESS)
         return fail(ctx, DIP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %dx%d pitch %zu box %dx%d",
                     (int)r, v.width, v.height, v.pitch, box_words, box_rows);
-    img->tmaps.push_back(key);
-    *out = &img->tmaps.back().map;
+    if (root->tmaps.size() >= 256) root->tmaps.clear();  // a caller sweeping thousands of distinct views: start over
+    root->tmaps.push_back(key);
+    *out = &root->tmaps.back().map;  // valid until the next get_tmap on this allocation (launches copy it by value)
     return DIP_OK;
 }
 
@@ -287,6 +292,7 @@ int dip_image_create_batch(dip_ctx* ctx, int w, int h, int c, int frames, dip_im
     v.rowbytes = w * c;
     v.pitch = round_up((size_t)v.rowbytes, 16);
     v.frame_stride = v.pitch * (size_t)h;
+    v.pad_writable = true;
     const size_t bytes = v.frame_stride * (size_t)frames;
     cudaSetDevice(ctx->device);
     cudaError_t e = cudaMalloc(&im->alloc, bytes);
@@ -319,7 +325,7 @@ int dip_image_wrap(dip_ctx* ctx, void* p, int w, int h, int c, int frames, size_
     dip_image* im = nullptr;
     int rc = new_image(ctx, &im);
     if (rc != DIP_OK) return rc;
-    im->v = ImgView{static_cast<uint8_t*>(p), pitch, frame_stride, w, h, c, frames, w * c};
+    im->v = ImgView{static_cast<uint8_t*>(p), pitch, frame_stride, w, h, c, frames, w * c, false};
     *out = im;
     return DIP_OK;
 }
@@ -457,20 +463,25 @@ int enqueue_upload(dip_ctx* ctx, const ImgView& v, const uint8_t* host, size_t h
     if (is_pinned(host))
         return copy_2d(ctx, ctx->upload, v.base, v.pitch, v.frame_stride, host, host_pitch, host_pitch * (size_t)v.height, rowb,
                        v.height, v.frames, cudaMemcpyHostToDevice);
-    // pageable: stage row slices through two pinned slots, copy of slice k overlaps staging of k+1
+    // pageable: stage slices through two pinned slots, copy of slice k overlaps staging of k+1.  A slice is a run of
+    // whole rows, or -- when one row is longer than a staging slot -- a run of bytes within one row.
+    const size_t cols_per_slice = std::min(rowb, ctx->stage_bytes);
     const int rows_per_slice = (int)std::max<size_t>(1, ctx->stage_bytes / rowb);
     int slot = 0;
     for (int f = 0; f < v.frames; ++f) {
         for (int y = 0; y < v.height; y += rows_per_slice) {
             const int rows = std::min(rows_per_slice, v.height - y);
-            DIP_CUDA(ctx, cudaEventSynchronize(ctx->stage_up_free[slot]));
-            uint8_t* st = ctx->stage_up[slot];
-            const uint8_t* hsrc = host + host_pitch * ((size_t)f * v.height + y);
-            host_copy_rows(st, rowb, hsrc, host_pitch, rowb, rows);
-            DIP_CUDA(ctx, cudaMemcpy2DAsync(v.base + v.frame_stride * (size_t)f + v.pitch * (size_t)y, v.pitch, st, rowb, rowb,
-                                            rows, cudaMemcpyHostToDevice, ctx->upload));
-            DIP_CUDA(ctx, cudaEventRecord(ctx->stage_up_free[slot], ctx->upload));
-            slot ^= 1;
+            for (size_t x = 0; x < rowb; x += cols_per_slice) {
+                const size_t nb = std::min(cols_per_slice, rowb - x);   // == rowb unless a row exceeds the slot
+                DIP_CUDA(ctx, cudaEventSynchronize(ctx->stage_up_free[slot]));
+                uint8_t* st = ctx->stage_up[slot];
+                const uint8_t* hsrc = host + host_pitch * ((size_t)f * v.height + y) + x;
+                host_copy_rows(st, nb, hsrc, host_pitch, nb, rows);
+                DIP_CUDA(ctx, cudaMemcpy2DAsync(v.base + v.frame_stride * (size_t)f + v.pitch * (size_t)y + x, v.pitch, st, nb, nb,
+                                                rows, cudaMemcpyHostToDevice, ctx->upload));
+                DIP_CUDA(ctx, cudaEventRecord(ctx->stage_up_free[slot], ctx->upload));
+                slot ^= 1;
+            }
         }
     }
     return DIP_OK;
@@ -486,26 +497,30 @@ int enqueue_download(dip_ctx* ctx, const ImgView& v, uint8_t* host, size_t host_
     // pageable destination: D2H into pinned slots, drain slot k while slot k+1 is in flight.
     // The host memcpy needs the data, so this path completes before returning.
     *completed = true;
+    const size_t cols_per_slice = std::min(rowb, ctx->stage_bytes);   // a row longer than a slot is cut into byte runs
     const int rows_per_slice = (int)std::max<size_t>(1, ctx->stage_bytes / rowb);
-    struct Pending { uint8_t* hdst; int rows; bool live; } pend[dip_ctx::kSlots] = {};
+    struct Pending { uint8_t* hdst; size_t nb; int rows; bool live; } pend[dip_ctx::kSlots] = {};
     int slot = 0;
     auto drain = [&](int s) -> int {
         if (!pend[s].live) return DIP_OK;
         DIP_CUDA(ctx, cudaEventSynchronize(ctx->stage_dn_done[s]));
-        host_copy_rows(pend[s].hdst, host_pitch, ctx->stage_dn[s], rowb, rowb, pend[s].rows);
+        host_copy_rows(pend[s].hdst, host_pitch, ctx->stage_dn[s], pend[s].nb, pend[s].nb, pend[s].rows);
         pend[s].live = false;
         return DIP_OK;
     };
     for (int f = 0; f < v.frames; ++f) {
         for (int y = 0; y < v.height; y += rows_per_slice) {
             const int rows = std::min(rows_per_slice, v.height - y);
-            int rc = drain(slot);
-            if (rc != DIP_OK) return rc;
-            DIP_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_dn[slot], rowb, v.base + v.frame_stride * (size_t)f + v.pitch * (size_t)y,
-                                            v.pitch, rowb, rows, cudaMemcpyDeviceToHost, ctx->download));
-            DIP_CUDA(ctx, cudaEventRecord(ctx->stage_dn_done[slot], ctx->download));
-            pend[slot] = Pending{host + host_pitch * ((size_t)f * v.height + y), rows, true};
-            slot ^= 1;
+            for (size_t x = 0; x < rowb; x += cols_per_slice) {
+                const size_t nb = std::min(cols_per_slice, rowb - x);
+                int rc = drain(slot);
+                if (rc != DIP_OK) return rc;
+                DIP_CUDA(ctx, cudaMemcpy2DAsync(ctx->stage_dn[slot], nb, v.base + v.frame_stride * (size_t)f + v.pitch * (size_t)y + x,
+                                                v.pitch, nb, rows, cudaMemcpyDeviceToHost, ctx->download));
+                DIP_CUDA(ctx, cudaEventRecord(ctx->stage_dn_done[slot], ctx->download));
+                pend[slot] = Pending{host + host_pitch * ((size_t)f * v.height + y) + x, nb, rows, true};
+                slot ^= 1;
+            }
         }
     }
     for (int s = 0; s < dip_ctx::kSlots; ++s) {
@@ -533,6 +548,7 @@ int dip_upload(dip_ctx* ctx, dip_image* dst_view, const uint8_t* host, size_t ho
     if (dst->copy_pending) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->upload, dst->copy_done, 0));
     int rc = enqueue_upload(ctx, v, host, host_pitch);
     if (rc != DIP_OK) return rc;
+    if ((rc = ensure_copy_event(ctx, dst)) != DIP_OK) return rc;
     DIP_CUDA(ctx, cudaEventRecord(dst->copy_done, ctx->upload));
     dst->copy_pending = true;
     return DIP_OK;
@@ -553,6 +569,7 @@ int dip_download(dip_ctx* ctx, const dip_image* src_c, uint8_t* host, size_t hos
     int rc = enqueue_download(ctx, v, host, host_pitch, &completed);
     if (rc != DIP_OK) return rc;
     if (!completed) {
+        if ((rc = ensure_copy_event(ctx, src)) != DIP_OK) return rc;
         DIP_CUDA(ctx, cudaEventRecord(src->copy_done, ctx->download));
         src->copy_pending = true;
     }
@@ -668,6 +685,7 @@ int dip_image_ipc_import(dip_ctx* ctx, const dip_ipc_handle* h, int w, int hgt, 
     if (rc != DIP_OK) { cudaIpcCloseMemHandle(p); return rc; }
     (*out)->alloc = p;
     (*out)->ipc_mapped = true;
+    (*out)->v.pad_writable = true;  // the exporter's whole library-owned allocation: its row padding is padding here too
     return DIP_OK;
 }
 

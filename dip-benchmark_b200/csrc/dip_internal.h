@@ -25,9 +25,17 @@ struct ImgView {
     size_t frame_stride;  // bytes between frames (multiple of 16)
     int width, height, channels, frames;
     int rowbytes;         // width * channels
+    // The bytes between the end of a row and the next 16-byte boundary are padding the kernels may overwrite (library-owned
+    // allocations).  False for dip_image_wrap: there they can be the caller's pixels (a region of interest of a wider image).
+    bool pad_writable;
 };
 
+// A cached TMA descriptor.  The cache lives on the ROOT allocation (root_of) and is keyed by the view's geometry, so the
+// short-lived frame / row views the pipelines create per chunk find the descriptor their predecessor encoded.
 struct TmapKey {
+    const uint8_t* base;
+    size_t pitch, frame_stride;
+    int rowbytes, height, frames;
     int box_words, box_rows;
     CUtensorMap map;
 };
@@ -45,7 +53,7 @@ struct dip_image {
     // A copy (upload/download/halo) touching this image is outstanding on a copy stream.
     cudaEvent_t copy_done = nullptr;
     bool copy_pending = false;
-    std::vector<dip::TmapKey> tmaps;  // cached TMA descriptors of this view
+    std::vector<dip::TmapKey> tmaps;  // cached TMA descriptors of this allocation's views (used on the root image only)
 };
 
 struct dip_ctx {
@@ -252,8 +260,8 @@ inline dip_image* root_of(dip_image* im) {
     return im;
 }
 
-// true when the bytes between the end of a row and the next 16-byte boundary do NOT belong to the image
-inline bool exact_rows(const ImgView& v) { return v.pitch != (((size_t)v.rowbytes + 15) & ~(size_t)15); }
+// true when a row's last, partial 16-byte chunk must be stored byte-exactly (the bytes behind it are not ours to write)
+inline bool exact_rows(const ImgView& v) { return (v.rowbytes & 15) != 0 && !v.pad_writable; }
 
 inline RowGeom full_geom(const dip_image* src) {
     return RowGeom{0, src->v.height, 0, src->v.height, 0};

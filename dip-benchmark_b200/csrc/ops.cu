@@ -51,10 +51,9 @@ dip_op make_op(int kind) {
     return o;
 }
 
-const RefOp* reference_ops() {
-    static RefOp ops[12];
-    static bool init = false;
-    if (!init) {
+struct RefOps {
+    RefOp ops[12];
+    RefOps() {
         ops[0] = {"Copy", "copy", make_op(DIP_OP_COPY)};
         ops[1] = {"Inversion", "inversion", make_op(DIP_OP_INVERT)};
         ops[2] = {"Grayscale", "grayscale", make_op(DIP_OP_GRAYSCALE)};
@@ -75,9 +74,12 @@ const RefOp* reference_ops() {
         ops[10] = {"Convolution (1x5+5x1 Gaussian Blur Kernel)", "convolution-gaussian-blur-5x5-separated", make_op(DIP_OP_CONVOLVE_SEPARABLE)};
         ops[10].op.kernel = kBlur5Sep; ops[10].op.kernel_col = kBlur5Sep; ops[10].op.kw = 5; ops[10].op.kh = 5;
         ops[11] = {"Gaussian Blur (3x3 Kernel)", "gaussian-blur-3x3", make_op(DIP_OP_GAUSSIAN_BLUR3X3)};
-        init = true;
     }
-    return ops;
+};
+
+const RefOp* reference_ops() {
+    static const RefOps table;  // C++11 magic static: initialised once, also when several threads (one ctx each) race here
+    return table.ops;
 }
 
 }  // namespace
@@ -201,16 +203,21 @@ int plan_chain(dip_ctx* ctx, const dip_op* ops, int n, int channels, std::vector
     return DIP_OK;
 }
 
-int ensure_scratch(dip_ctx* ctx, const dip_image* like) {
+// The ctx-owned intermediate stack of dip_apply_chain: same frame geometry as `like`, at least as many frames (a
+// pipeline's partial last chunk reuses the full-chunk stack instead of reallocating it on every run).  *out is a view
+// of exactly like->frames frames that the caller destroys.
+int ensure_scratch(dip_ctx* ctx, const dip_image* like, dip_image** out) {
     dip_image* s = ctx->chain_scratch;
-    if (s && s->v.width == like->v.width && s->v.height == like->v.height && s->v.channels == like->v.channels && s->v.frames == like->v.frames)
-        return DIP_OK;
-    if (s) {
-        DIP_CUDA(ctx, cudaStreamSynchronize(ctx->compute));  // kernels may still be reading the old one
-        dip_image_destroy(s);
-        ctx->chain_scratch = nullptr;
+    if (!(s && s->v.width == like->v.width && s->v.height == like->v.height && s->v.channels == like->v.channels && s->v.frames >= like->v.frames)) {
+        if (s) {
+            DIP_CUDA(ctx, cudaStreamSynchronize(ctx->compute));  // kernels may still be reading the old one
+            dip_image_destroy(s);
+            ctx->chain_scratch = nullptr;
+        }
+        int rc = dip_image_create_batch(ctx, like->v.width, like->v.height, like->v.channels, like->v.frames, &ctx->chain_scratch);
+        if (rc != DIP_OK) return rc;
     }
-    return dip_image_create_batch(ctx, like->v.width, like->v.height, like->v.channels, like->v.frames, &ctx->chain_scratch);
+    return dip_image_view(ctx, ctx->chain_scratch, 0, like->v.frames, out);
 }
 
 int run_stencil_pass(dip_ctx* ctx, const dip_op& op, const ChainPass& ps, const dip_image* src, dip_image* dst) {
@@ -268,20 +275,21 @@ int dip_apply_chain(dip_ctx* ctx, const dip_op* ops, int n, const dip_image* src
     bool any_stencil = false;
     for (const ChainPass& p : plan) any_stencil |= p.kind != ChainPass::Point;
     if (any_stencil && (rc = check_pair(ctx, src, dst, false)) != DIP_OK) return rc;
-    if (k > 1 && (rc = ensure_scratch(ctx, src)) != DIP_OK) return rc;
-    if ((rc = begin_op(ctx, src, dst)) != DIP_OK) return rc;
+    dip_image* scratch = nullptr;
+    if (k > 1 && (rc = ensure_scratch(ctx, src, &scratch)) != DIP_OK) return rc;
+    rc = begin_op(ctx, src, dst);
     // pass j (1-based) writes dst when k - j is even, the scratch stack otherwise: the last pass lands in dst and no
     // pass reads what it writes
     const dip_image* in = src;
-    for (int j = 1; j <= k; ++j) {
+    for (int j = 1; j <= k && rc == DIP_OK; ++j) {
         const ChainPass& p = plan[j - 1];
-        dip_image* out = ((k - j) & 1) ? ctx->chain_scratch : dst;
+        dip_image* out = ((k - j) & 1) ? scratch : dst;
         if (p.kind == ChainPass::Point) rc = launch_point_chain(ctx, in->v, out->v, p.pre, p.gray, p.post);
         else rc = run_stencil_pass(ctx, ops[p.op_index], p, in, out);
-        if (rc != DIP_OK) return rc;
         in = out;
     }
-    return DIP_OK;
+    dip_image_destroy(scratch);
+    return rc;
 }
 
 // One-shot form of the pipeline below.
@@ -413,34 +421,37 @@ int dip_pipeline_run(dip_pipeline* p, const uint8_t* host_in, int in_ring, int f
     int rc = DIP_OK;
     int slot = 0;
     bool used[2] = {false, false};
+    // CUDA calls inside the loop record their error in rc and fall through, so that the per-chunk views are released
+    // and the trailing dip_sync still runs (host buffers must not be in flight when the call returns)
+    auto cu = [&](cudaError_t e, const char* what) { if (e != cudaSuccess && rc == DIP_OK) rc = fail_cuda(ctx, e, what, __FILE__, __LINE__); };
     for (int f0 = 0; f0 < frames && rc == DIP_OK; f0 += p->chunk, slot ^= 1) {
         const int n = std::min(p->chunk, frames - f0);
         dip_image* iv = nullptr;
         if ((rc = dip_image_view(ctx, p->in[slot], 0, n, &iv)) != DIP_OK) break;
         // H2D: wait until the kernels of two chunks ago released this input slot
-        if (used[slot]) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->upload, p->in_free[slot], 0));
-        rc = enqueue_upload(ctx, iv->v, host_in + frame_bytes * (size_t)(f0 % in_ring), frame_bytes / p->h);
+        if (used[slot]) cu(cudaStreamWaitEvent(ctx->upload, p->in_free[slot], 0), "cudaStreamWaitEvent(upload, in_free)");
+        if (rc == DIP_OK) rc = enqueue_upload(ctx, iv->v, host_in + frame_bytes * (size_t)(f0 % in_ring), frame_bytes / p->h);
         if (rc == DIP_OK) {
-            DIP_CUDA(ctx, cudaEventRecord(p->in_ready[slot], ctx->upload));
-            DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, p->in_ready[slot], 0));
+            cu(cudaEventRecord(p->in_ready[slot], ctx->upload), "cudaEventRecord(in_ready)");
+            cu(cudaStreamWaitEvent(ctx->compute, p->in_ready[slot], 0), "cudaStreamWaitEvent(compute, in_ready)");
         }
         for (int o = 0; o < p->n_out && rc == DIP_OK; ++o) {
             const size_t idx = (size_t)slot * p->n_out + o;
             dip_image* ov = nullptr;
             if ((rc = dip_image_view(ctx, p->out[idx], 0, n, &ov)) != DIP_OK) break;
             // the kernel may overwrite this output slot only after its previous download finished
-            if (used[slot]) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, p->out_free[idx], 0));
-            rc = p->chain ? dip_apply_chain(ctx, p->ops.data(), p->n_ops, iv, ov) : dip_apply(ctx, &p->ops[o], iv, ov);
+            if (used[slot]) cu(cudaStreamWaitEvent(ctx->compute, p->out_free[idx], 0), "cudaStreamWaitEvent(compute, out_free)");
+            if (rc == DIP_OK) rc = p->chain ? dip_apply_chain(ctx, p->ops.data(), p->n_ops, iv, ov) : dip_apply(ctx, &p->ops[o], iv, ov);
             if (rc == DIP_OK) {
-                DIP_CUDA(ctx, cudaEventRecord(p->out_ready[idx], ctx->compute));
-                DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->download, p->out_ready[idx], 0));
+                cu(cudaEventRecord(p->out_ready[idx], ctx->compute), "cudaEventRecord(out_ready)");
+                cu(cudaStreamWaitEvent(ctx->download, p->out_ready[idx], 0), "cudaStreamWaitEvent(download, out_ready)");
                 bool completed = false;
-                rc = enqueue_download(ctx, ov->v, host_out[o] + frame_bytes * (size_t)(f0 % out_ring), frame_bytes / p->h, &completed);
-                if (rc == DIP_OK) DIP_CUDA(ctx, cudaEventRecord(p->out_free[idx], ctx->download));
+                if (rc == DIP_OK) rc = enqueue_download(ctx, ov->v, host_out[o] + frame_bytes * (size_t)(f0 % out_ring), frame_bytes / p->h, &completed);
+                if (rc == DIP_OK) cu(cudaEventRecord(p->out_free[idx], ctx->download), "cudaEventRecord(out_free)");
             }
             dip_image_destroy(ov);
         }
-        if (rc == DIP_OK) DIP_CUDA(ctx, cudaEventRecord(p->in_free[slot], ctx->compute));
+        if (rc == DIP_OK) cu(cudaEventRecord(p->in_free[slot], ctx->compute), "cudaEventRecord(in_free)");
         used[slot] = true;
         dip_image_destroy(iv);
     }

@@ -244,7 +244,7 @@ __global__ void __launch_bounds__(kThreads) synth_kernel(ImgView dst, uint32_t s
         w[k] = word;
     }
     store16(dst.base + f * dst.frame_stride + y * dst.pitch + 16 * vx, make_uint4(w[0], w[1], w[2], w[3]),
-            chunk_valid(16 * vx, dst.rowbytes, dst.pitch != (((size_t)dst.rowbytes + 15) & ~(size_t)15)));
+            chunk_valid(16 * vx, dst.rowbytes, !dst.pad_writable));
 }
 
 __global__ void __launch_bounds__(kThreads) checksum_kernel(ImgView src, int vec_per_row, size_t vec_per_frame, uint64_t first_row,
@@ -277,8 +277,8 @@ __global__ void __launch_bounds__(kThreads) checksum_kernel(ImgView src, int vec
 
 bool dense_pair(const ImgView& a, const ImgView& b) {
     const size_t padded = ((size_t)a.rowbytes + 15) & ~(size_t)15;
-    auto dense = [&](const ImgView& v) {
-        return v.pitch == padded && (v.frames == 1 || v.frame_stride == v.pitch * (size_t)v.height);
+    auto dense = [&](const ImgView& v) {  // one flat byte stream whose row padding may be written
+        return v.pitch == padded && !exact_rows(v) && (v.frames == 1 || v.frame_stride == v.pitch * (size_t)v.height);
     };
     return dense(a) && dense(b);
 }

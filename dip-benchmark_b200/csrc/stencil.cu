@@ -39,7 +39,8 @@ namespace dip {
 namespace {
 
 // Development knobs (dip_debug_set): "tile_rows" 0 = automatic, 64 or 32 forces the tile height.
-struct Knobs { int tile_rows = 0; };
+// "int_math" 1 = the packed-integer forms of the two separable Gaussians instead of the packed-half ones (A/B only).
+struct Knobs { int tile_rows = 0; int int_math = 0; };
 Knobs g_knobs;
 
 // One warp band of the fused Gaussian -> erosion kernel below.  EDGE: the tile touches the image rim, so Gaussian
@@ -271,11 +272,12 @@ int launch_tiled_op(dip_ctx* ctx, int op, const dip_image* src, dip_image* dst, 
         maps = &moved;
     }
     if (maps && !(maps->pre.identity() && maps->post.identity())) return launch_tiled_mapped(ctx, op, src, dst, g, *maps);
+    if (g_knobs.int_math) op = op == kConv3Sep ? kConv3SepI : op == kConv5Sep ? kConv5SepI : op;
     switch (op) {
 #define DIP_T(OP) case OP: return launch_tiled_c<OP>(ctx, src, dst, g);
         DIP_T(kErodeSq3) DIP_T(kErodeCross3) DIP_T(kDilateSq3) DIP_T(kDilateCross3) DIP_T(kConv3) DIP_T(kConv3Sep) DIP_T(kGauss3)
         DIP_T(kConv5) DIP_T(kConv5Sep) DIP_T(kErodeRow3) DIP_T(kErodeCol3) DIP_T(kDilateRow3) DIP_T(kDilateCol3) DIP_T(kConvRow3)
-        DIP_T(kConvCol3) DIP_T(kConvRow5) DIP_T(kConvCol5)
+        DIP_T(kConvCol3) DIP_T(kConvRow5) DIP_T(kConvCol5) DIP_T(kConv3SepI) DIP_T(kConv5SepI)
 #undef DIP_T
     }
     return fail(ctx, DIP_ERR_ARG, "bad tiled op %d", op);
@@ -524,6 +526,7 @@ extern "C" {
 int dip_debug_set(const char* key, int value) {
     if (!key) return fail(nullptr, DIP_ERR_ARG, "null key");
     if (!strcmp(key, "tile_rows")) g_knobs.tile_rows = value;
+    else if (!strcmp(key, "int_math")) g_knobs.int_math = value;
     else if (!strcmp(key, "no_pad")) g_no_occupancy_pad = value != 0;
     else return fail(nullptr, DIP_ERR_ARG, "unknown knob %s", key);
     return DIP_OK;

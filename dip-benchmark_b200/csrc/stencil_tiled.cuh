@@ -38,15 +38,27 @@ enum StencilOp {
     kConvCol3 = 14,   // along y
     kConvRow5 = 15,   // RNE([1 4 6 4 1]/16) along x
     kConvCol5 = 16,   // along y
+    // the packed-integer forms of kConv3Sep / kConv5Sep (the shipped ones compute in packed half precision, see
+    // "packed-half arithmetic" below); kept for A/B measurements behind the development knob "int_math"
+    kConv3SepI = 17,
+    kConv5SepI = 18,
 };
 
 __host__ __device__ constexpr bool op_is_row_only(int op) { return op == kErodeRow3 || op == kDilateRow3 || op == kConvRow3 || op == kConvRow5; }
 __host__ __device__ constexpr bool op_is_col_only(int op) { return op == kErodeCol3 || op == kDilateCol3 || op == kConvCol3 || op == kConvCol5; }
-__host__ __device__ constexpr int op_taps(int op) { return (op == kConv5 || op == kConv5Sep || op == kConvRow5 || op == kConvCol5) ? 2 : 1; }
+__host__ __device__ constexpr int op_taps(int op) { return (op == kConv5 || op == kConv5Sep || op == kConv5SepI || op == kConvRow5 || op == kConvCol5) ? 2 : 1; }
 __host__ __device__ constexpr int op_radius_x(int op) { return op_is_col_only(op) ? 0 : op_taps(op); }
 __host__ __device__ constexpr int op_radius_y(int op) { return op_is_row_only(op) ? 0 : op_taps(op); }
 __host__ __device__ constexpr bool op_is_dilate(int op) { return op == kDilateSq3 || op == kDilateCross3 || op == kDilateRow3 || op == kDilateCol3; }
 __host__ __device__ constexpr bool op_is_morph(int op) { return op <= kDilateCross3 || (op >= kErodeRow3 && op <= kDilateCol3); }
+
+// Resident CTAs per SM the register allocation must allow (0 = whatever ptxas picks).  The packed-half 1x5+5x1 kernel
+// comes out at 89 registers (5 CTAs of 4 warps) without the bound; it is issue-bound and wants the 6 the tile allows.
+__host__ __device__ constexpr int op_min_ctas(int op) { return op == kConv5Sep ? 6 : 1; }
+#ifndef DIP_EVEN_PRMT5
+#define DIP_EVEN_PRMT5 6
+#endif
+constexpr int kEvenPrmt5 = DIP_EVEN_PRMT5;  // packed-half 1x5+5x1: words per row whose even bytes come from a PRMT
 
 struct StencilParams {
     ImgView dst;
@@ -205,10 +217,69 @@ __device__ __forceinline__ uint32_t round_keep_scaled(uint32_t r) {
     return (__umulhi(r & (0x00010001u << S), 1u << (32 - S)) + r) & keep;  // LOP3 + LEA.HI + LOP3
 }
 
+// ---- packed-half arithmetic ---------------------------------------------------------------------------------------
+// A u8 in a 16-bit lane IS the half-precision number b * 2^-24 (a subnormal), so the unpacked even / odd byte streams
+// can be fed to HFMA2 as they are.  Two properties make the separable Gaussians exact in half precision:
+//   * every integer of magnitude <= 2048 (in units of u = 2^-24) is a half, so a [1 4 6 4 1] sum (<= 4080) is exact once
+//     it is centred: S' = S - 2048 = ((6 c - 2048) + 4 (b + d)) + (a + e), each step inside [-2048, 2047];
+//   * the subnormal ulp is exactly u, so ONE fused multiply-add  S' * 2^-4 + 128 u  rounds S / 16 to an integer with
+//     round-half-even -- the reference's cvRound -- and leaves the u8 result as the lane's bit pattern.
+// That replaces the LOP3 + LEA.HI (+ LOP3) rounding sequences on the integer ALU pipe, which is what bounds these kernels
+// (tools/ubench/half_pipes.cu: HFMA2 issues at the IMAD rate on the FMA pipe, also on subnormals, and the rounding
+// identity holds for all 4096 sums; the small non-negative sums a + e, b + d stay integer adds on the ALU pipe).
+__device__ __forceinline__ uint32_t hfma2(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t d;
+    asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+__device__ __forceinline__ uint32_t hadd2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+__device__ __forceinline__ uint32_t hmul2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
+}
+constexpr uint32_t kH2 = 0x40004000u;        // half2(2)
+constexpr uint32_t kH4 = 0x44004400u;        // half2(4)
+constexpr uint32_t kH6 = 0x46004600u;        // half2(6)
+constexpr uint32_t kHQuarter = 0x34003400u;  // half2(1/4)
+constexpr uint32_t kH16th = 0x2C002C00u;     // half2(1/16)
+constexpr uint32_t kHNeg2048u = 0x88008800u; // half2(-2048 * 2^-24) = -2^-13
+constexpr uint32_t kH128u = 0x00800080u;     // half2(128 * 2^-24): the bit pattern of the byte 128
+// RNE((a + 4 b + 6 c + 4 d + e) / 16) per lane; ae = a + e and bd = b + d are plain integer sums (<= 510)
+__device__ __forceinline__ uint32_t half_gauss5(uint32_t ae, uint32_t bd, uint32_t c) {
+    const uint32_t s = hadd2(hfma2(bd, kH4, hfma2(c, kH6, kHNeg2048u)), ae);  // S - 2048, exact
+    return hfma2(s, kH16th, kH128u);
+}
+// RNE((a + 2 b + c) / 4) per lane; ac = a + c (<= 510)
+__device__ __forceinline__ uint32_t half_gauss3(uint32_t ac, uint32_t b) { return hmul2(hfma2(b, kH2, ac), kHQuarter); }
+
+template <int C>
+__device__ __forceinline__ void hgauss5_half(const Row8& r, Acc8& h) {
+#define DIP_H5H(j)                                                                                                   \
+    h.v[2 * j] = half_gauss5(pair_at<4 * j - 2 * C>(r) + pair_at<4 * j + 2 * C>(r), pair_at<4 * j - C>(r) + pair_at<4 * j + C>(r), r.e[2 + j]); \
+    h.v[2 * j + 1] = half_gauss5(pair_at<4 * j + 1 - 2 * C>(r) + pair_at<4 * j + 1 + 2 * C>(r), pair_at<4 * j + 1 - C>(r) + pair_at<4 * j + 1 + C>(r), r.o[2 + j]);
+    DIP_H5H(0) DIP_H5H(1) DIP_H5H(2) DIP_H5H(3)
+#undef DIP_H5H
+}
+template <int C>
+__device__ __forceinline__ void hgauss3_half(const Row8& r, Acc8& h) {
+#define DIP_H3H(j)                                                                                   \
+    h.v[2 * j] = half_gauss3(pair_at<4 * j - C>(r) + pair_at<4 * j + C>(r), r.e[2 + j]);               \
+    h.v[2 * j + 1] = half_gauss3(pair_at<4 * j + 1 - C>(r) + pair_at<4 * j + 1 + C>(r), r.o[2 + j]);
+    DIP_H3H(0) DIP_H3H(1) DIP_H3H(2) DIP_H3H(3)
+#undef DIP_H3H
+}
+
 // PRE: the chain's map in front of a convolution is applied to the words as they are unpacked (halo words are
 // mapped by both neighbours; cheaper than a pass over the tile with its barrier).  Erosion / dilation never carry one:
 // launch_tiled_op moves it behind the op.
-template <bool PRE = false>
+// EVEN_PRMT: how many of the 8 words get their even bytes by a second PRMT (integer ALU pipe) instead of the IMAD (FMA
+// pipe) -- the packed-half kernels keep the FMA pipe busier than the ALU pipe, the integer ones the other way round.
+template <bool PRE = false, int EVEN_PRMT = 0>
 __device__ __forceinline__ void load_row(const uint8_t* rowp, Row8& r, const StencilParams* sp = nullptr) {
     const uint2 a = *reinterpret_cast<const uint2*>(rowp - 8);
     const uint4 b = *reinterpret_cast<const uint4*>(rowp);
@@ -218,7 +289,7 @@ __device__ __forceinline__ void load_row(const uint8_t* rowp, Row8& r, const Ste
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
         r.o[i] = odd_bytes(w[i]);
-        r.e[i] = even_bytes(w[i], r.o[i]);
+        r.e[i] = i < EVEN_PRMT ? __byte_perm(w[i], 0u, 0x4240) : even_bytes(w[i], r.o[i]);
     }
 }
 
@@ -326,12 +397,10 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
 #pragma unroll
                 for (int j = 0; j < 4; ++j) out[j] = pack_lo(h.v[2 * j], h.v[2 * j + 1]);
             } else {
-                constexpr uint32_t scale = OP == kConvRow3 ? 64u : 16u;  // sum * scale has the result in the high byte
-                if constexpr (OP == kConvRow3) hsum3<C>(row, h, 0u);
-                else hsum5<C>(row, h, 0u);
+                if constexpr (OP == kConvRow3) hgauss3_half<C>(row, h);
+                else hgauss5_half<C>(row, h);
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    out[j] = pack_hi(rne_finish(h.v[2 * j] * scale + 0x007F007Fu), rne_finish(h.v[2 * j + 1] * scale + 0x007F007Fu));
+                for (int j = 0; j < 4; ++j) out[j] = pack_lo(h.v[2 * j], h.v[2 * j + 1]);
             }
             put16<CLIP, MAPPED>(dptr + (size_t)i * p.dst.pitch, make_uint4(out[0], out[1], out[2], out[3]), valid, p);
         }
@@ -357,19 +426,18 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
 #pragma unroll
                 for (int k = 0; k < 8; ++k) {
                     if constexpr (op_is_morph(OP)) res[k] = mnmx3<op_is_dilate(OP)>(w0.v[k], w1.v[k], w2.v[k]);
-                    else res[k] = rne_finish((w0.v[k] + w2.v[k]) * 64u + w1.v[k] * 128u + 0x007F007Fu);
+                    else res[k] = half_gauss3(w0.v[k] + w2.v[k], w1.v[k]);
                 }
                 w0 = w1; w1 = w2;
             } else {
                 load_own(colp + (i + 4) * kRowBytes, w4);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    res[k] = rne_finish((w0.v[k] + w4.v[k]) * 16u + (w1.v[k] + w3.v[k]) * 64u + w2.v[k] * 96u + 0x007F007Fu);
+                    res[k] = half_gauss5(w0.v[k] + w4.v[k], w1.v[k] + w3.v[k], w2.v[k]);
                 w0 = w1; w1 = w2; w2 = w3; w3 = w4;
             }
             uint4 o;
-            if constexpr (op_is_morph(OP)) o = make_uint4(pack_lo(res[0], res[1]), pack_lo(res[2], res[3]), pack_lo(res[4], res[5]), pack_lo(res[6], res[7]));
-            else o = make_uint4(pack_hi(res[0], res[1]), pack_hi(res[2], res[3]), pack_hi(res[4], res[5]), pack_hi(res[6], res[7]));
+            o = make_uint4(pack_lo(res[0], res[1]), pack_lo(res[2], res[3]), pack_lo(res[4], res[5]), pack_lo(res[6], res[7]));
             put16<CLIP, MAPPED>(dptr + (size_t)i * p.dst.pitch, o, valid, p);
         }
     } else if constexpr (op_is_morph(OP)) {
@@ -414,16 +482,58 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
             h1 = h2;
             put16<CLIP, MAPPED>(dptr + (size_t)i * p.dst.pitch, make_uint4(out[0], out[1], out[2], out[3]), valid, p);
         }
+    } else if constexpr (OP == kConv3Sep) {
+        // RNE([1 2 1]/4) rows -> u8 -> RNE([1 2 1]/4) columns in packed half precision: h* hold the u8 rows i-1, i, i+1
+        Acc8 h0, h1, h2;
+        Row8 row;
+        auto hpass = [&](const uint8_t* rp, Acc8& h) {
+            load_row<PRE>(rp, row, &p);
+            hgauss3_half<C>(row, h);
+        };
+        hpass(colp, h0);
+        hpass(colp + kRowBytes, h1);
+#pragma unroll 3
+        for (int i = 0; i < nrows; ++i) {
+            hpass(colp + (i + 2) * kRowBytes, h2);
+            uint32_t res[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) res[k] = half_gauss3(h0.v[k] + h2.v[k], h1.v[k]);
+            put16<CLIP, MAPPED>(dptr + (size_t)i * p.dst.pitch,
+                    make_uint4(pack_lo(res[0], res[1]), pack_lo(res[2], res[3]), pack_lo(res[4], res[5]), pack_lo(res[6], res[7])), valid, p);
+            h0 = h1; h1 = h2;
+        }
+    } else if constexpr (OP == kConv5Sep) {
+        // RNE([1 4 6 4 1]/16) rows -> u8 -> RNE([1 4 6 4 1]/16) columns in packed half precision
+        Acc8 h0, h1, h2, h3, h4;
+        Row8 row;
+        auto hpass = [&](const uint8_t* rp, Acc8& h) {
+            load_row<PRE, kEvenPrmt5>(rp, row, &p);
+            hgauss5_half<C>(row, h);
+        };
+        hpass(colp, h0);
+        hpass(colp + kRowBytes, h1);
+        hpass(colp + 2 * kRowBytes, h2);
+        hpass(colp + 3 * kRowBytes, h3);
+#pragma unroll 5
+        for (int i = 0; i < nrows; ++i) {
+            hpass(colp + (i + 4) * kRowBytes, h4);
+            uint32_t res[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) res[k] = half_gauss5(h0.v[k] + h4.v[k], h1.v[k] + h3.v[k], h2.v[k]);
+            put16<CLIP, MAPPED>(dptr + (size_t)i * p.dst.pitch,
+                    make_uint4(pack_lo(res[0], res[1]), pack_lo(res[2], res[3]), pack_lo(res[4], res[5]), pack_lo(res[6], res[7])), valid, p);
+            h0 = h1; h1 = h2; h2 = h3; h3 = h4;
+        }
     } else if constexpr (op_taps(OP) == 1) {
         // 3-tap Gaussians.  h* hold the horizontal pass of rows i-1, i, i+1.
-        const uint32_t hbias = OP == kConv3Sep ? reg_const<0x00010001u>() : 0u;
+        const uint32_t hbias = OP == kConv3SepI ? reg_const<0x00010001u>() : 0u;
         const uint32_t vbias = reg_const<(OP == kGauss3 ? 0x00800080u : 0x007F007Fu)>();
         Acc8 h0, h1, h2;
         Row8 row;
         auto hpass = [&](const uint8_t* rp, Acc8& h) {
             load_row<PRE>(rp, row, &p);
             hsum3<C>(row, h, hbias);
-            if constexpr (OP == kConv3Sep) {
+            if constexpr (OP == kConv3SepI) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) h.v[k] = round_keep_scaled<2>(h.v[k]);  // 4 * RNE(sum / 4)
             }
@@ -448,14 +558,14 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
         }
     } else {
         // 5-tap Gaussians.  h* hold the horizontal pass of rows i-2 .. i+2.
-        const uint32_t hbias = OP == kConv5Sep ? reg_const<0x00070007u>() : 0u;
+        const uint32_t hbias = OP == kConv5SepI ? reg_const<0x00070007u>() : 0u;
         const uint32_t vbias = reg_const<0x007F007Fu>();
         Acc8 h0, h1, h2, h3, h4;
         Row8 row;
         auto hpass = [&](const uint8_t* rp, Acc8& h) {
             load_row<PRE>(rp, row, &p);
             hsum5<C>(row, h, hbias);
-            if constexpr (OP == kConv5Sep) {
+            if constexpr (OP == kConv5SepI) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) h.v[k] = round_keep_scaled<4>(h.v[k]);  // 16 * RNE(sum / 16)
             }
@@ -472,7 +582,7 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
             for (int k = 0; k < 8; ++k) {
                 // X = sum of [1 4 6 4 1] x h <= 65280: result in the high byte after RNE
                 // the separable variant (two roundings) is the most ALU-bound: all of its vertical adds go to the FMA pipe
-                const uint32_t x = OP == kConv5Sep
+                const uint32_t x = OP == kConv5SepI
                                        ? padd(h0.v[k], padd(h4.v[k], 4u * padd(h1.v[k], h3.v[k]) + (6u * h2.v[k] + vbias)))
                                        : (h0.v[k] + h4.v[k]) + (4u * padd(h1.v[k], h3.v[k]) + (6u * h2.v[k] + vbias));
                 res[k] = rne_finish(x);
@@ -526,7 +636,7 @@ __device__ __forceinline__ void process_tile(uint8_t* tile, const StencilParams&
 
 // ---- the tiled kernel -------------------------------------------------------------------------
 template <int OP, int C, int R, int kWarps, bool MAPPED>
-__global__ void __launch_bounds__(kWarps * 32) stencil_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
+__global__ void __launch_bounds__(kWarps * 32, op_min_ctas(OP)) stencil_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
     constexpr int r = op_radius_y(OP);   // halo rows
     constexpr int TH = kWarps * R;
     constexpr int ROWS = TH + 2 * r;
@@ -591,7 +701,8 @@ int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGe
     static std::atomic<uint64_t> attr_set{0};  // per instantiation, one bit per device
     const uint64_t dev_bit = 1ull << (ctx->device & 63);
     if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
-        DIP_CUDA(ctx, cudaFuncSetAttribute(stencil_kernel<OP, C, R, kWarps, MAPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        // the limit covers both settings of the "no_pad" knob, whichever the first launch used
+        DIP_CUDA(ctx, cudaFuncSetAttribute(stencil_kernel<OP, C, R, kWarps, MAPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(kPadded, kTileSmem)));
         attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
     DIP_CUDA(ctx, launch_kernel(stencil_kernel<OP, C, R, kWarps, MAPPED>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames), dim3(kThreads), smem_bytes, ctx->compute, *map, p));

@@ -241,11 +241,20 @@ int main(int argc, char** argv) {
     fs::path inpath(pos[0]);
     if (!inpath.has_filename()) { std::fprintf(stderr, "Error: [INPUT IMAGE] must be an image file, e.g. JPG, PGM, PPM\n"); return 2; }  // sycl:417-421
     fs::path outpath(pos[1]);
+    if (outpath.has_filename()) {  // like the reference, the output directory is spelled with a trailing separator   sycl:422-426
+        std::fprintf(stderr, "Error: [OUTPUT PATH] must be a path to output image file\n");
+        return 3;
+    }
 
     dip_ctx* ctx = nullptr;
-    if (dip_init(&ctx, device) < 0) {                                                                     // sycl:428-432
+    int n_devices = 0;
+    if (dip_device_count(&n_devices) < 0 || n_devices == 0) {                                             // sycl:428-432
         std::fprintf(stderr, "Error: No GPU device found, aborting (%s)\n", dip_last_error_string(nullptr));
         return 4;
+    }
+    if (dip_init(&ctx, device) < 0) {  // a GPU is there but this library cannot use it (not sm_100, bad --device)      sycl:434-438
+        std::fprintf(stderr, "Error: Device does not support this library (sm_100a only), aborting (%s)\n", dip_last_error_string(nullptr));
+        return 5;
     }
     dip_device_info info;
     dip_get_device_info(ctx, &info);

@@ -58,18 +58,20 @@ def test_full_size_known_answers(orc, kat):
 
 
 def test_fundus_known_answers(orc, kat):
-    """The HRF fundus image (BASELINE.json config 0-2); decoded by cv2 or PIL, hash-gated."""
-    path = os.path.join(ROOT, "data", "fundus.jpg")
-    img = None
-    try:
-        import cv2
-        img = cv2.imread(path)
-    except Exception:  # noqa: BLE001
-        pass
-    if img is None or digest(img)["sha256_16"] != kat["inputs"]["A_fundus"]["sha256_16"]:
-        pytest.skip("JPEG decoder differs from the one that made the known answers")
+    """The HRF fundus image (BASELINE.json configs 0-2).  The committed lossless crop of the reference decode
+    (tests/golden/make_fundus_crop.py) always runs; the full-size hashes run when this box's JPEG decoder is the one that
+    made them (the decoded pixels differ otherwise) -- nothing is skipped."""
+    crop = np.load(os.path.join(ROOT, "tests", "golden", "fundus_crop.npz"))
     for prefix, fn in orc.OPERATIONS:
-        assert digest(fn(img)) == kat["outputs"]["A_fundus"][prefix], prefix
+        assert np.array_equal(fn(crop["input"]), crop[prefix]), f"fundus crop {prefix}"
+    import cv2
+    img = cv2.imread(os.path.join(ROOT, "data", "fundus.jpg"))
+    assert img is not None and img.shape == (2336, 3504, 3)
+    if digest(img)["sha256_16"] == kat["inputs"]["A_fundus"]["sha256_16"]:
+        for prefix, fn in orc.OPERATIONS:
+            assert digest(fn(img)) == kat["outputs"]["A_fundus"][prefix], prefix
+    else:  # another libjpeg: the crop of the reference decode must at least be close to what this one decodes
+        assert np.abs(img[1090:1250, 2350:2590].astype(int) - crop["input"].astype(int)).max() <= 8
 
 
 def test_grayscale_exhaustive_formula(orc):
