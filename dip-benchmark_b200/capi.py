@@ -44,6 +44,10 @@ class IpcHandle(C.Structure):
     _fields_ = [("bytes", C.c_ubyte * 64)]
 
 
+class PeerRows(C.Structure):
+    _fields_ = [("image", C.c_void_p), ("src_row0", C.c_int), ("image_row0", C.c_int), ("rows", C.c_int)]
+
+
 def lib_path() -> str:
     return _LIB
 
@@ -121,6 +125,10 @@ def lib() -> C.CDLL:
         "dip_run_chain_host": ([vp, vp, i, i, i, i, P(Op), i, vp, i], i),
         "dip_pipeline_run": ([vp, vp, i, i, P(vp), i], i),
         "dip_pipeline_destroy": ([vp], i),
+        "dip_graph_begin": ([vp], i),
+        "dip_graph_end": ([vp, P(vp)], i),
+        "dip_graph_launch": ([vp, vp], i),
+        "dip_graph_destroy": ([vp], i),
         "dip_mark": ([vp, i], i),
         "dip_elapsed": ([vp, i, i, P(C.c_float)], i),
         "dip_timer_start": ([vp], i),
@@ -136,6 +144,11 @@ def lib() -> C.CDLL:
         "dip_copy_rows": ([vp, vp, i, vp, i, i], i),
         "dip_halo_fence": ([vp], i),
         "dip_apply_rows": ([vp, P(Op), vp, i, i, i, i, vp, i], i),
+        "dip_apply_rows_peer": ([vp, P(Op), vp, i, i, i, i, vp, i, P(PeerRows), P(PeerRows)], i),
+        "dip_flags_create": ([vp, i, P(vp)], i),
+        "dip_flag_signal": ([vp, vp, i, C.c_uint32], i),
+        "dip_flag_wait": ([vp, vp, i, C.c_uint32], i),
+        "dip_flag_read": ([vp, vp, i, P(C.c_uint32)], i),
         "dip_debug_set": ([C.c_char_p, i], i),
     }
     for name, (args, res) in sig.items():

@@ -56,6 +56,13 @@ struct dip_image {
     std::vector<dip::TmapKey> tmaps;  // cached TMA descriptors of this allocation's views (used on the root image only)
 };
 
+struct dip_graph {
+    dip_ctx* ctx = nullptr;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t kernels = 0;  // kernel launches recorded (added to the ctx's launch count on every replay)
+};
+
 struct dip_ctx {
     int device = -1;
     cudaStream_t compute = nullptr;  // kernels
@@ -83,6 +90,8 @@ struct dip_ctx {
     int d_checksums_cap = 0;
     std::vector<cudaEvent_t> marks;
     dip_image* chain_scratch = nullptr;  // intermediate stack of dip_apply_chain (library-owned, reallocated on shape change)
+    bool capturing = false;              // between dip_graph_begin and dip_graph_end: kernels are recorded, not run
+    uint64_t capture_launches0 = 0;
     std::string last_error;
 };
 
@@ -233,6 +242,10 @@ int launch_fill(dip_ctx* ctx, uint8_t* p, size_t bytes, uint32_t value);
 // row coordinates are written to dst rows starting at dst_y0.
 struct RowGeom {
     int valid_y0, valid_y1, out_y0, out_y1, dst_y0;
+    // dip_apply_rows_peer: source rows [peer_*_y0, peer_*_y1) are read from a neighbour GPU's band (see StencilParams)
+    const uint8_t* peer_top = nullptr;
+    const uint8_t* peer_bot = nullptr;
+    int peer_top_y0 = 0, peer_top_y1 = 0, peer_bot_y0 = 0, peer_bot_y1 = 0;
 };
 enum class Morph { Erode, Dilate };
 // `maps` (optional): per-byte maps fused into the launch; only the 2-D tiled kernels take them (stencil_takes_maps)

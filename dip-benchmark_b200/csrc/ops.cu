@@ -209,6 +209,7 @@ int plan_chain(dip_ctx* ctx, const dip_op* ops, int n, int channels, std::vector
 int ensure_scratch(dip_ctx* ctx, const dip_image* like, dip_image** out) {
     dip_image* s = ctx->chain_scratch;
     if (!(s && s->v.width == like->v.width && s->v.height == like->v.height && s->v.channels == like->v.channels && s->v.frames >= like->v.frames)) {
+        if (ctx->capturing) return fail(ctx, DIP_ERR_UNSUPPORTED, "run this chain once before recording it: its scratch stack is allocated on first use");
         if (s) {
             DIP_CUDA(ctx, cudaStreamSynchronize(ctx->compute));  // kernels may still be reading the old one
             dip_image_destroy(s);
@@ -309,12 +310,52 @@ int dip_run_ops_host(dip_ctx* ctx, const uint8_t* host_in, int w, int h, int c, 
 
 }  // extern "C"
 
+namespace {
+
+// Translates a dip_peer_rows into the kernel's view: the peer byte that corresponds to byte 0 of source row 0.
+int set_peer(dip_ctx* ctx, const dip_image* src, const dip_peer_rows* pr, const uint8_t** base, int* y0, int* y1) {
+    if (!pr || !pr->image || pr->rows == 0) return DIP_OK;
+    const ImgView &a = src->v, &b = pr->image->v;
+    if (pr->rows < 0 || pr->src_row0 < 0 || pr->src_row0 + pr->rows > a.height || pr->image_row0 < 0 || pr->image_row0 + pr->rows > b.height)
+        return fail(ctx, DIP_ERR_ARG, "peer rows out of bounds");
+    if (a.rowbytes != b.rowbytes || a.channels != b.channels || a.frames != b.frames || a.pitch != b.pitch ||
+        (a.frames > 1 && a.frame_stride != b.frame_stride))
+        return fail(ctx, DIP_ERR_SHAPE, "a peer band must have the source's row length, pitch and frame layout");
+    *base = b.base + ((ptrdiff_t)pr->image_row0 - (ptrdiff_t)pr->src_row0) * (ptrdiff_t)a.pitch;
+    *y0 = pr->src_row0;
+    *y1 = pr->src_row0 + pr->rows;
+    return DIP_OK;
+}
+
+int apply_rows_impl(dip_ctx* ctx, const dip_op* op, const dip_image* src, int valid_row0, int valid_rows, int out_row0, int out_rows,
+                    dip_image* dst, int dst_row0, const dip_peer_rows* above, const dip_peer_rows* below);
+
+}  // namespace
+
 extern "C" int dip_apply_rows(dip_ctx* ctx, const dip_op* op, const dip_image* src, int valid_row0, int valid_rows,
                               int out_row0, int out_rows, dip_image* dst, int dst_row0) {
+    return apply_rows_impl(ctx, op, src, valid_row0, valid_rows, out_row0, out_rows, dst, dst_row0, nullptr, nullptr);
+}
+
+extern "C" int dip_apply_rows_peer(dip_ctx* ctx, const dip_op* op, const dip_image* src, int valid_row0, int valid_rows,
+                                   int out_row0, int out_rows, dip_image* dst, int dst_row0, const dip_peer_rows* above,
+                                   const dip_peer_rows* below) {
+    return apply_rows_impl(ctx, op, src, valid_row0, valid_rows, out_row0, out_rows, dst, dst_row0, above, below);
+}
+
+namespace {
+
+int apply_rows_impl(dip_ctx* ctx, const dip_op* op, const dip_image* src, int valid_row0, int valid_rows, int out_row0, int out_rows,
+                    dip_image* dst, int dst_row0, const dip_peer_rows* above, const dip_peer_rows* below) {
     if (!ctx || !op || !src || !dst) return fail(ctx, DIP_ERR_ARG, "null argument");
     if (out_rows < 1 || valid_rows < 1) return fail(ctx, DIP_ERR_ARG, "empty row range");
-    const RowGeom g{valid_row0, valid_row0 + valid_rows, out_row0, out_row0 + out_rows, dst_row0};
-    int rc = begin_op(ctx, src, dst);
+    RowGeom g{valid_row0, valid_row0 + valid_rows, out_row0, out_row0 + out_rows, dst_row0};
+    int rc = set_peer(ctx, src, above, &g.peer_top, &g.peer_top_y0, &g.peer_top_y1);
+    if (rc == DIP_OK) rc = set_peer(ctx, src, below, &g.peer_bot, &g.peer_bot_y0, &g.peer_bot_y1);
+    if (rc != DIP_OK) return rc;
+    if ((g.peer_top || g.peer_bot) && op->kind != DIP_OP_GAUSS5X5_ERODE3X3 && stencil_tiled_op(*op) < 0)
+        return fail(ctx, DIP_ERR_UNSUPPORTED, "in-kernel peer rows need a tiled stencil kernel; use dip_copy_rows for this operation");
+    rc = begin_op(ctx, src, dst);
     if (rc != DIP_OK) return rc;
     switch (op->kind) {
         case DIP_OP_ERODE: return stencil_morph(ctx, Morph::Erode, src, dst, op->mask, op->mask_w, op->mask_h, g);
@@ -341,6 +382,8 @@ extern "C" int dip_apply_rows(dip_ctx* ctx, const dip_op* op, const dip_image* s
     dip_image_destroy(dv);
     return rc;
 }
+
+}  // namespace
 
 extern "C" {
 

@@ -163,6 +163,11 @@ __global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_co
     __syncthreads();
     mbar_wait(bar, 0);
     const bool border = gx0 <= 0 || gx0 + kTileBytes + 2 * C > p.rowbytes || ytop < p.valid_y0 || ytop + ROWS > p.valid_y1;
+    if (tile_has_peer_rows<ROWS>(p, ytop)) {  // rows of a neighbour GPU's band: read over NVLink, no exchange step
+        __syncthreads();
+        patch_peer_rows<ROWS, kThreads>(tile, p, gx0, ytop, f);
+        if (!border) __syncthreads();
+    }
     if (border) {
         __syncthreads();
         patch_borders<kConv5, C, ROWS, kThreads>(tile, p, gx0, ytop);
@@ -206,6 +211,7 @@ int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const 
     p.tiles_x = (src->v.rowbytes + (kTileBytes - 32) - 1) / (kTileBytes - 32);
     p.tiles_y = (g.out_y1 - g.out_y0 + TO - 1) / TO;
     p.dst_exact = exact_rows(dst->v);
+    fill_peer_params(p, src, g);
     if (MAPPED && maps) {
         p.has_pre = !maps->pre.identity();
         p.pre = map_params(maps->pre);

@@ -69,6 +69,14 @@ struct StencilParams {
     int dst_y0;              // dst row receiving out_y0
     int tiles_x, tiles_y;
     bool dst_exact;          // dst rows are not padded to 16 bytes (wrapped region of interest)
+    // Mosaic bands (dip_apply_rows_peer): source rows [peer_top_y0, peer_top_y1) / [peer_bot_y0, peer_bot_y1) are not in
+    // this GPU's band buffer but in the neighbour's, which is mapped into this process (CUDA IPC, NVLink): the CTAs whose
+    // tile covers such rows read them straight from the peer.  peer_* point at the peer byte that corresponds to byte 0
+    // of source row 0 of frame 0 (same pitch and frame stride as the source), so the address arithmetic is the source's.
+    const uint8_t* peer_top;
+    const uint8_t* peer_bot;
+    int peer_top_y0, peer_top_y1, peer_bot_y0, peer_bot_y1;
+    size_t src_pitch, src_frame_stride;
     // MAPPED kernels (dip_apply_chain): per-byte map of the source words as they are unpacked / of the result words
     bool has_pre;
     MapParams pre, post;
@@ -365,6 +373,34 @@ __device__ void patch_borders(uint8_t* tile, const StencilParams& p, int bx0, in
     }
 }
 
+// Tile rows that belong to a neighbour GPU's band: 16-byte loads from the peer mapping (ld.global.cv: never a stale
+// line of an earlier step), stored over the tile rows the TMA load filled from the local buffer's unused halo rows.
+// Columns outside [0, padded row) are zero like TMA's out-of-bounds fill; the column patch that follows reflects them.
+template <int ROWS, int kThreads>
+__device__ __forceinline__ void patch_peer_rows(uint8_t* tile, const StencilParams& p, int bx0, int ytop, int f) {
+    const int row_padded = (p.rowbytes + 15) & ~15;
+    constexpr int vec_per_row = kRowBytes / 16;
+    auto pull = [&](const uint8_t* peer, int y0, int y1) {
+        const int t0 = max(y0 - ytop, 0), t1 = min(y1 - ytop, ROWS);
+        for (int i = threadIdx.x; i < (t1 - t0) * vec_per_row; i += kThreads) {
+            const int t = t0 + i / vec_per_row, vx = i % vec_per_row;
+            const int x = bx0 - kHalo + 16 * vx;
+            uint4 v = make_uint4(0u, 0u, 0u, 0u);
+            if (x >= 0 && x < row_padded)
+                v = __ldcv(reinterpret_cast<const uint4*>(peer + (size_t)f * p.src_frame_stride + (size_t)(ytop + t) * p.src_pitch + x));
+            *reinterpret_cast<uint4*>(tile + t * kRowBytes + 16 * vx) = v;
+        }
+    };
+    if (p.peer_top && ytop < p.peer_top_y1 && ytop + ROWS > p.peer_top_y0) pull(p.peer_top, p.peer_top_y0, p.peer_top_y1);
+    if (p.peer_bot && ytop < p.peer_bot_y1 && ytop + ROWS > p.peer_bot_y0) pull(p.peer_bot, p.peer_bot_y0, p.peer_bot_y1);
+}
+// block-uniform: does this tile hold rows that live on a neighbour GPU?
+template <int ROWS>
+__device__ __forceinline__ bool tile_has_peer_rows(const StencilParams& p, int ytop) {
+    return (p.peer_top && ytop < p.peer_top_y1 && ytop + ROWS > p.peer_top_y0) ||
+           (p.peer_bot && ytop < p.peer_bot_y1 && ytop + ROWS > p.peer_bot_y0);
+}
+
 // ---- the arithmetic of one warp band: the thread walks down its 16-byte column --------------------
 // FULL = the band has all R rows (compile-time trip count: the row loops unroll by the period of the
 // register window without a remainder loop); otherwise `nrows_rt` rows.
@@ -608,6 +644,11 @@ __device__ __forceinline__ void process_tile(uint8_t* tile, const StencilParams&
     const int ytop = y0 - r;            // source row held by tile row 0
     const bool border = (rx > 0 && (bx0 == 0 || bx0 + kTileBytes + rx * C > p.rowbytes)) ||
                         (r > 0 && (ytop < p.valid_y0 || ytop + ROWS > p.valid_y1));
+    if (tile_has_peer_rows<ROWS>(p, ytop)) {
+        __syncthreads();
+        patch_peer_rows<ROWS, kThreads>(tile, p, bx0, ytop, f);
+        if (!border) __syncthreads();
+    }
     if (border) {
         __syncthreads();
         patch_borders<OP, C, ROWS, kThreads>(tile, p, bx0, ytop);
@@ -665,6 +706,14 @@ __global__ void __launch_bounds__(kWarps * 32, op_min_ctas(OP)) stencil_kernel(c
 
 bool g_no_occupancy_pad = false;  // development knob "no_pad"
 
+// fills the source-side fields every tiled launch shares
+inline void fill_peer_params(StencilParams& p, const dip_image* src, const RowGeom& g) {
+    p.src_pitch = src->v.pitch;
+    p.src_frame_stride = src->v.frame_stride;
+    p.peer_top = g.peer_top; p.peer_top_y0 = g.peer_top_y0; p.peer_top_y1 = g.peer_top_y1;
+    p.peer_bot = g.peer_bot; p.peer_bot_y0 = g.peer_bot_y0; p.peer_bot_y1 = g.peer_bot_y1;
+}
+
 template <int OP, int C, int R, int kWarps, bool MAPPED>
 int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps) {
     constexpr int r = op_radius_y(OP);
@@ -691,6 +740,7 @@ int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGe
     p.tiles_x = (src->v.rowbytes + kTileBytes - 1) / kTileBytes;
     p.tiles_y = (g.out_y1 - g.out_y0 + TH - 1) / TH;
     p.dst_exact = exact_rows(dst->v);
+    fill_peer_params(p, src, g);
     if (MAPPED && maps) {
         p.has_pre = !maps->pre.identity();
         p.pre = map_params(maps->pre);

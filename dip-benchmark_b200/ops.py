@@ -112,6 +112,21 @@ class Image:
         return self
 
 
+class Graph:
+    """A recorded sequence of operations (dip_graph_*): launch() replays it with one CUDA graph launch."""
+
+    def __init__(self, ctx: "Context", handle: int):
+        self.ctx, self._h = ctx, C.c_void_p(handle)
+
+    def launch(self):
+        check(lib().dip_graph_launch(self.ctx._h, self._h), self.ctx._h)
+
+    def close(self):
+        if self._h:
+            lib().dip_graph_destroy(self._h)
+            self._h = C.c_void_p(None)
+
+
 class Context:
     """One GPU, one compute stream, two copy streams (include/dip.h lifecycle group)."""
 
@@ -271,6 +286,35 @@ class Context:
         check(lib().dip_apply_rows(self._h, C.byref(op), src._h, valid_row0, valid_rows, out_row0, out_rows, dst._h,
                                    dst_row0), self._h)
 
+    def apply_rows_peer(self, op: capi.Op, src: Image, valid_row0: int, valid_rows: int, out_row0: int, out_rows: int,
+                        dst: Image, dst_row0: int = 0, above=None, below=None):
+        """dip_apply_rows_peer: `above` / `below` = (neighbour's mapped band image, first src row it serves, its row, rows)."""
+        def peer(t):
+            if t is None:
+                return None
+            img, src_row0, image_row0, rows = t
+            return capi.PeerRows(img._h, src_row0, image_row0, rows)
+        pa, pb = peer(above), peer(below)
+        check(lib().dip_apply_rows_peer(self._h, C.byref(op), src._h, valid_row0, valid_rows, out_row0, out_rows, dst._h, dst_row0,
+                                        C.byref(pa) if pa else None, C.byref(pb) if pb else None), self._h)
+
+    # -- step flags between neighbouring bands (include/dip.h "Step flags") -----------------------------
+    def flags(self, count: int) -> Image:
+        h = C.c_void_p()
+        check(lib().dip_flags_create(self._h, count, C.byref(h)), self._h)
+        return Image(self, h.value)
+
+    def flag_signal(self, flags: Image, index: int, value: int):
+        check(lib().dip_flag_signal(self._h, flags._h, index, value & 0xFFFFFFFF), self._h)
+
+    def flag_wait(self, flags: Image, index: int, value: int):
+        check(lib().dip_flag_wait(self._h, flags._h, index, value & 0xFFFFFFFF), self._h)
+
+    def flag_read(self, flags: Image, index: int) -> int:
+        v = C.c_uint32(0)
+        check(lib().dip_flag_read(self._h, flags._h, index, C.byref(v)), self._h)
+        return int(v.value)
+
     def run_ops_host(self, host_in: np.ndarray, ops, host_out: list[np.ndarray], chunk_frames: int = 4):
         """Upload -> every op -> download, pipelined over three streams (dip_run_ops_host)."""
         a = host_in
@@ -291,6 +335,15 @@ class Context:
 
     def pipeline(self, width: int, height: int, channels: int, chunk_frames: int, ops, chain: bool = False) -> "Pipeline":
         return Pipeline(self, width, height, channels, chunk_frames, ops, chain=chain)
+
+    # -- CUDA-graph replay (include/dip.h "CUDA-graph replay") -------------------------------------------
+    def graph_begin(self):
+        check(lib().dip_graph_begin(self._h), self._h)
+
+    def graph_end(self) -> "Graph":
+        h = C.c_void_p()
+        check(lib().dip_graph_end(self._h, C.byref(h)), self._h)
+        return Graph(self, h.value)
 
     # -- timing ---------------------------------------------------------------------------------
     def mark(self, slot: int):

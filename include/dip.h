@@ -248,6 +248,18 @@ DIP_API int dip_pipeline_create_chain(dip_ctx* ctx, int width, int height, int c
 DIP_API int dip_run_chain_host(dip_ctx* ctx, const uint8_t* host_in, int width, int height, int channels, int frames,
                                const dip_op* ops, int n_ops, uint8_t* host_out, int chunk_frames);
 
+/* ---- CUDA-graph replay (SURVEY.md 8f rank 4 "graph capture"): record what the calls between dip_graph_begin and
+ *      dip_graph_end enqueue on the compute stream -- any dip_* operation, chain or row-band call; not transfers, not
+ *      dip_sync -- and replay it with ONE launch per dip_graph_launch.  The reference's measure_time loops
+ *      (opencv:33-35, sycl:33-37) enqueue thousands of identical few-microsecond kernels; recorded in blocks, their host
+ *      cost per call drops to the graph launch divided by the block size.  The images used while recording must stay
+ *      alive (and keep their contents' meaning) for every replay; a chain's scratch stack must exist (run it once). */
+typedef struct dip_graph dip_graph;
+DIP_API int dip_graph_begin(dip_ctx* ctx);
+DIP_API int dip_graph_end(dip_ctx* ctx, dip_graph** graph);
+DIP_API int dip_graph_launch(dip_ctx* ctx, dip_graph* graph);
+DIP_API int dip_graph_destroy(dip_graph* graph);
+
 /* ---- device-side timing on the ctx's compute stream (measure_time opencv:26-38,
  *      sycl:25-39 use a host clock; these are CUDA events) --------------------------- */
 DIP_API int dip_timer_start(dip_ctx* ctx);
@@ -299,8 +311,42 @@ DIP_API int dip_apply_rows(dip_ctx* ctx, const dip_op* op, const dip_image* src,
                            int valid_rows, int out_row0, int out_rows, dip_image* dst,
                            int dst_row0);
 
+/* The same as dip_apply_rows, with the halo rows read from the neighbour GPUs INSIDE the kernel (SURVEY.md 8e
+ * "preferred, fused"): source rows [src_row0, src_row0+rows) are not taken from src but from rows [image_row0, ...)
+ * of `image`, the neighbour's band buffer mapped with dip_image_ipc_import (same width, channels and pitch as src).
+ * Only the CTAs whose tile covers such rows touch the peer (16-byte loads over NVLink into their shared-memory tile);
+ * there is no exchange step, no copy into src's halo rows and no extra pass over HBM.  Tiled stencil kernels only
+ * (the benchmark's masks / kernels, the 1-D passes, dip_gauss5x5_erode3x3); DIP_ERR_UNSUPPORTED otherwise. */
+typedef struct dip_peer_rows {
+    const dip_image* image; /* NULL: no neighbour on this side */
+    int src_row0;           /* first row of src served by the neighbour */
+    int image_row0;         /* the row of `image` that is src row src_row0 */
+    int rows;
+} dip_peer_rows;
+DIP_API int dip_apply_rows_peer(dip_ctx* ctx, const dip_op* op, const dip_image* src, int valid_row0,
+                                int valid_rows, int out_row0, int out_rows, dip_image* dst, int dst_row0,
+                                const dip_peer_rows* above, const dip_peer_rows* below);
+
+/* Step flags for bands whose input changes from step to step (each rank's result becomes its next input).  A flag
+ * array is a tiny library-owned image (`count` 32-bit words, zeroed) that neighbours map with dip_image_ipc_export /
+ * _import (width 4*count, height 1, 1 channel).
+ *   dip_flag_signal: after everything enqueued so far on the compute stream has finished, store `value` into word
+ *                    `index` (release, system scope); `flags` may be the neighbour's mapped array (a store over NVLink).
+ *   dip_flag_wait:   the compute stream waits until word `index` >= value (cuStreamWaitValue32 -- a stream operation,
+ *                    no kernel spins); `flags` must live on this ctx's GPU.
+ *   dip_flag_read:   host read-back (synchronous), for tests.
+ * Protocol of MosaicBand (mosaic.py): step k reads buffer k%2 and writes (k+1)%2; before it a rank waits for
+ * flag[neighbour] >= k-1 (the neighbour finished step k-1: its rows of buffer k%2 are written, and it no longer reads
+ * this rank's buffer (k+1)%2); after it, it signals k into both neighbours' arrays. */
+DIP_API int dip_flags_create(dip_ctx* ctx, int count, dip_image** flags);
+DIP_API int dip_flag_signal(dip_ctx* ctx, dip_image* flags, int index, uint32_t value);
+DIP_API int dip_flag_wait(dip_ctx* ctx, const dip_image* flags, int index, uint32_t value);
+DIP_API int dip_flag_read(dip_ctx* ctx, const dip_image* flags, int index, uint32_t* value);
+
 /* ---- development hook: kernel-selection knobs for A/B measurements inside one process.
- * keys: "tile_rows" (stencil tile height: 0 = automatic, 60 = stack tiles, 32 = single-image tiles), "fused_rows" (fused chain: 0 = 4-warp CTAs, 2 = 2-warp CTAs).  Not needed by applications. */
+ * keys: "tile_rows" (stencil tile height: 0 = automatic, >= 60 the stack tiles, < 60 the single-image tiles),
+ * "no_pad" (1 = do not pad shared memory to limit the resident tiles of the HBM-bound stencils), "int_math" (1 = the
+ * packed-integer forms of the separable Gaussians instead of the packed-half ones).  Not needed by applications. */
 DIP_API int dip_debug_set(const char* key, int value);
 
 #ifdef __cplusplus

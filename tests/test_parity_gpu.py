@@ -261,15 +261,18 @@ def test_error_behaviour(ctx, dip):
     ctx.sync()
 
 
-def test_mosaic_bands_with_halo_exchange_single_gpu(ctx, dip, orc):
-    """BASELINE.json config 5 at reduced size: bands + pulled halos (dip_copy_rows) == whole-image oracle,
-    and the band checksums add up to the checksum of the whole result."""
+@pytest.mark.parametrize("halo", ["kernel", "copy"])
+@pytest.mark.parametrize("fused", [False, True])
+def test_mosaic_bands_with_halo_exchange_single_gpu(ctx, dip, orc, halo, fused):
+    """BASELINE.json config 5 at reduced size: bands whose rim CTAs read the neighbours' rows in the kernel
+    (dip_apply_rows_peer) or that pull them first (dip_copy_rows) == whole-image oracle, and the band checksums add up
+    to the checksum of the whole result."""
     width, rows = 2100, 777
     whole = orc.synth(width, rows, 1, seed=4, frame=0)
     want = orc.erode(orc.filter2d(whole, orc.BLUR_5X5), orc.SQUARE_MASK)
     want_cs = orc.checksum(want)
     for world in (1, 2, 3, 5):
-        bands = [dip.mosaic.MosaicBand(ctx, width, rows, world, r) for r in range(world)]
+        bands = [dip.mosaic.MosaicBand(ctx, width, rows, world, r, fused=fused, halo=halo) for r in range(world)]
         for b in bands:
             b.fill_synthetic(seed=4)
         for b in bands:
@@ -282,6 +285,63 @@ def test_mosaic_bands_with_halo_exchange_single_gpu(ctx, dip, orc):
         assert sum(b.checksum() for b in bands) & 0xFFFFFFFFFFFFFFFF == want_cs, world
         for b in bands:
             b.close()
+
+
+@pytest.mark.parametrize("halo", ["kernel", "copy"])
+def test_mosaic_iterated_steps_under_the_flag_protocol(ctx, dip, orc, halo):
+    """iterate=True: every step's result is the next step's input (two band buffers used in turn), ordered between
+    neighbouring bands by dip_flag_signal / dip_flag_wait.  Three steps == the oracle applied three times."""
+    width, rows, steps = 1500, 640, 3
+    whole = orc.synth(width, rows, 1, seed=9, frame=0)
+    want = whole
+    for _ in range(steps):
+        want = orc.erode(orc.filter2d(want, orc.BLUR_5X5), orc.SQUARE_MASK)
+    for fused in (True, False):
+        for world in (1, 2, 4):
+            bands = [dip.mosaic.MosaicBand(ctx, width, rows, world, r, fused=fused, halo=halo, iterate=True) for r in range(world)]
+            for b in bands:
+                b.fill_synthetic(seed=9)
+            for b in bands:
+                b.connect_local(bands)
+            for s in range(steps):
+                for b in bands:
+                    b.step(overlap=(s % 2 == 0))
+            out = np.concatenate([b.result().download() for b in bands], axis=0)
+            assert np.array_equal(out, want), (fused, world)
+            if world > 1:   # every band saw its neighbours' last signal
+                ctx.sync()
+                assert ctx.flag_read(bands[0].flags, 1) == steps and ctx.flag_read(bands[-1].flags, 0) == steps
+            for b in bands:
+                b.close()
+
+
+@pytest.mark.parametrize("halo", ["kernel", "copy"])
+def test_mosaic_bands_in_two_processes_over_cuda_ipc(ctx, dip, orc, tmp_path, halo):
+    """The multi-process path bench.py uses under torchrun (MosaicBand.export_handle / connect: cudaIpcGetMemHandle /
+    cudaIpcOpenMemHandle), on the one GPU this box has: two processes, one band each, the neighbour's band buffer mapped
+    through its IPC handle; concatenated bands == whole-image oracle.  (The ranks order themselves with host-side
+    barriers here; kernels of two processes sharing one GPU must never wait on each other.)"""
+    import subprocess
+    import sys
+    width, rows = 1300, 500
+    worker = os.path.join(ROOT, "tests", "ipc_band_worker.py")
+    procs = [subprocess.Popen([sys.executable, worker, str(r), "2", str(tmp_path), str(width), str(rows), halo],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True) for r in range(2)]
+    outs = []
+    for p in procs:
+        try:
+            o, _ = p.communicate(timeout=240)
+        except subprocess.TimeoutExpired:
+            for q in procs:
+                q.kill()
+            raise
+        outs.append(o)
+    assert all(p.returncode == 0 for p in procs), "\n".join(outs)
+    whole = orc.synth(width, rows, 1, seed=6, frame=0)
+    for fused in (0, 1):
+        want = orc.erode(orc.filter2d(whole, orc.BLUR_5X5), orc.SQUARE_MASK)
+        got = np.concatenate([np.load(tmp_path / f"out{fused}_{r}.npy") for r in range(2)], axis=0)
+        assert np.array_equal(got, want), f"fused={fused}"
 
 
 @pytest.mark.parametrize("c", [1, 3, 4])
