@@ -231,7 +231,7 @@ int dip_shutdown(dip_ctx* ctx) {
     cudaStreamSynchronize(ctx->upload);
     cudaStreamSynchronize(ctx->download);
     cudaStreamSynchronize(ctx->halo);
-    if (ctx->chain_scratch) { dip_image_destroy(ctx->chain_scratch); ctx->chain_scratch = nullptr; }
+    for (dip_image*& sc : ctx->scratch) { dip_image_destroy(sc); sc = nullptr; }
     for (int i = 0; i < dip_ctx::kSlots; ++i) {
         if (ctx->stage_up[i]) cudaFreeHost(ctx->stage_up[i]);
         if (ctx->stage_dn[i]) cudaFreeHost(ctx->stage_dn[i]);

@@ -89,7 +89,9 @@ struct dip_ctx {
     uint64_t* d_checksums = nullptr;
     int d_checksums_cap = 0;
     std::vector<cudaEvent_t> marks;
-    dip_image* chain_scratch = nullptr;  // intermediate stack of dip_apply_chain (library-owned, reallocated on shape change)
+    // library-owned intermediate stacks (grown on shape change): [0] dip_apply_chain's ping-pong partner, [1] the `aux`
+    // image of the two-pass separable convolution (a chain may run such a convolution between its own two buffers)
+    dip_image* scratch[2] = {nullptr, nullptr};
     bool capturing = false;              // between dip_graph_begin and dip_graph_end: kernels are recorded, not run
     uint64_t capture_launches0 = 0;
     std::string last_error;
@@ -264,6 +266,19 @@ bool stencil_is_erode_sq3(const dip_op& op);  // 3x3 all-ones erosion (either fo
 // stencil_mapped.cu: tiled kernel `op` with the maps fused in
 int launch_tiled_mapped(dip_ctx* ctx, int op, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps& maps);
 int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps = nullptr);
+
+// A view of like->frames frames of the ctx-owned scratch stack `slot` (same frame geometry as `like`; allocated or grown on
+// first use).  The caller destroys the view.  Used by dip_apply_chain and by the two-pass separable convolution.
+int scratch_view(dip_ctx* ctx, int slot, const dip_image* like, dip_image** out);
+
+// stencil_generic.cu: arbitrary masks / kernels of up to 7 x 7 taps on the TMA tile.  `w[dy][k]` is the tap at row dy,
+// column k of the (kh x kw) mask or kernel, anchored at (kh/2, kw/2); morphology: non-zero = tap.  mode 0 erode,
+// 1 dilate, 2 correlation.
+struct SmallTaps {
+    float w[7][7];
+    int kh;
+};
+int launch_generic_tiled(dip_ctx* ctx, int mode, int kw, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps);
 
 // TMA descriptor of an image view seen as a (pitch/4 words, rows, frames) u32 tensor.
 int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out);

@@ -206,20 +206,26 @@ int plan_chain(dip_ctx* ctx, const dip_op* ops, int n, int channels, std::vector
 // The ctx-owned intermediate stack of dip_apply_chain: same frame geometry as `like`, at least as many frames (a
 // pipeline's partial last chunk reuses the full-chunk stack instead of reallocating it on every run).  *out is a view
 // of exactly like->frames frames that the caller destroys.
-int ensure_scratch(dip_ctx* ctx, const dip_image* like, dip_image** out) {
-    dip_image* s = ctx->chain_scratch;
+int ensure_scratch(dip_ctx* ctx, const dip_image* like, dip_image** out) { return dip::scratch_view(ctx, 0, like, out); }
+
+}  // namespace
+
+int dip::scratch_view(dip_ctx* ctx, int slot, const dip_image* like, dip_image** out) {
+    dip_image* s = ctx->scratch[slot];
     if (!(s && s->v.width == like->v.width && s->v.height == like->v.height && s->v.channels == like->v.channels && s->v.frames >= like->v.frames)) {
         if (ctx->capturing) return fail(ctx, DIP_ERR_UNSUPPORTED, "run this chain once before recording it: its scratch stack is allocated on first use");
         if (s) {
             DIP_CUDA(ctx, cudaStreamSynchronize(ctx->compute));  // kernels may still be reading the old one
             dip_image_destroy(s);
-            ctx->chain_scratch = nullptr;
+            ctx->scratch[slot] = nullptr;
         }
-        int rc = dip_image_create_batch(ctx, like->v.width, like->v.height, like->v.channels, like->v.frames, &ctx->chain_scratch);
+        int rc = dip_image_create_batch(ctx, like->v.width, like->v.height, like->v.channels, like->v.frames, &ctx->scratch[slot]);
         if (rc != DIP_OK) return rc;
     }
-    return dip_image_view(ctx, ctx->chain_scratch, 0, like->v.frames, out);
+    return dip_image_view(ctx, ctx->scratch[slot], 0, like->v.frames, out);
 }
+
+namespace {
 
 int run_stencil_pass(dip_ctx* ctx, const dip_op& op, const ChainPass& ps, const dip_image* src, dip_image* dst) {
     const RowGeom g = full_geom(src);

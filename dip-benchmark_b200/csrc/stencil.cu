@@ -40,7 +40,8 @@ namespace {
 
 // Development knobs (dip_debug_set): "tile_rows" 0 = automatic, 64 or 32 forces the tile height.
 // "int_math" 1 = the packed-integer forms of the two separable Gaussians instead of the packed-half ones (A/B only).
-struct Knobs { int tile_rows = 0; int int_math = 0; };
+// "direct_generic" 1 = arbitrary small masks / kernels through the direct kernel instead of the tiled generic one (A/B only).
+struct Knobs { int tile_rows = 0; int int_math = 0; int direct_generic = 0; };
 Knobs g_knobs;
 
 // One warp band of the fused Gaussian -> erosion kernel below.  EDGE: the tile touches the image rim, so Gaussian
@@ -375,6 +376,11 @@ int check_geom(dip_ctx* ctx, const dip_image* src, const dip_image* dst, const R
     return DIP_OK;
 }
 
+// can this view be a TMA tensor (16-byte aligned base, pitch and frame stride)?  Library-owned images always can.
+bool tma_ok(const dip_image* im) {
+    return !((reinterpret_cast<uintptr_t>(im->v.base) & 15) || (im->v.pitch & 15) || (im->v.frame_stride & 15));
+}
+
 // weights * scale are integers matching `pattern`?
 bool matches(const float* k, int n, const int* pattern, float scale) {
     for (int i = 0; i < n; ++i)
@@ -458,6 +464,13 @@ int stencil_morph(dip_ctx* ctx, Morph m, const dip_image* src, dip_image* dst, c
     const int top = classify_morph(m, mask, mw, mh);
     if (top >= 0) return launch_tiled_op(ctx, top, src, dst, g, maps);
     if (maps) return fail(ctx, DIP_ERR_UNSUPPORTED, "per-byte maps fuse into the tiled kernels only");
+    if (mw <= 7 && mh <= 7 && !g_knobs.direct_generic && tma_ok(src)) {  // small masks: the tiled generic kernel
+        SmallTaps t{};
+        t.kh = mh;
+        for (int j = 0; j < mh; ++j)
+            for (int i = 0; i < mw; ++i) t.w[j][i + std::max(1, mw / 2) - mw / 2] = mask[j * mw + i] ? 1.0f : 0.0f;
+        return launch_generic_tiled(ctx, dil ? 1 : 0, mw, src, dst, g, t);
+    }
     GenericParams p;
     fill_generic(p, src, dst, g, mw, mh);
     for (int j = 0; j < mh; ++j)
@@ -480,6 +493,13 @@ int stencil_convolve(dip_ctx* ctx, const dip_image* src, dip_image* dst, const f
     const int top = classify_convolve(k, kw, kh);
     if (top >= 0) return launch_tiled_op(ctx, top, src, dst, g, maps);
     if (maps) return fail(ctx, DIP_ERR_UNSUPPORTED, "per-byte maps fuse into the tiled kernels only");
+    if (kw <= 7 && kh <= 7 && !g_knobs.direct_generic && tma_ok(src)) {  // small kernels: the tiled generic kernel
+        SmallTaps t{};
+        t.kh = kh;
+        for (int j = 0; j < kh; ++j)
+            for (int i = 0; i < kw; ++i) t.w[j][i + std::max(1, kw / 2) - kw / 2] = k[j * kw + i];
+        return launch_generic_tiled(ctx, 2, kw, src, dst, g, t);
+    }
     GenericParams p;
     fill_generic(p, src, dst, g, kw, kh);
     for (int j = 0; j < kh; ++j)
@@ -500,9 +520,23 @@ int stencil_convolve_sep(dip_ctx* ctx, const dip_image* src, dip_image* dst, con
     if (rc != DIP_OK) return rc;
     const int top = classify_convolve_sep(krow, kw, kcol, kh);
     if (top >= 0) return launch_tiled_op(ctx, top, src, dst, g, maps);
-    return fail(ctx, DIP_ERR_UNSUPPORTED,
-                "fused separable convolution supports the binomial [1 2 1]/4 and [1 4 6 4 1]/16 kernels; "
-                "run two dip_convolve passes for other kernels");
+    // Any other pair of kernels: the reference's two calls through `aux` (opencv:84-90, sycl:347-356) -- a 1 x kw pass
+    // whose result is rounded and saturated to u8 exactly as `aux` is, then a kh x 1 pass -- with the ctx's scratch stack
+    // as `aux`.  The row pass also produces the rows the column pass reads above and below the requested range.
+    if (maps) return fail(ctx, DIP_ERR_UNSUPPORTED, "per-byte maps fuse into the tiled kernels only");
+    if (kw * 1 > kMaxTaps || kh * 1 > kMaxTaps || kw > 127 || kh > 127) return fail(ctx, DIP_ERR_UNSUPPORTED, "kernel longer than %d taps", kMaxTaps);
+    if (g.peer_top || g.peer_bot) return fail(ctx, DIP_ERR_UNSUPPORTED, "two-pass separable convolution cannot read peer rows");
+    dip_image* aux = nullptr;
+    if ((rc = scratch_view(ctx, 1, src, &aux)) != DIP_OK) return rc;
+    const int ry = kh / 2;
+    RowGeom g1 = g;
+    g1.out_y0 = std::max(g.valid_y0, g.out_y0 - ry);
+    g1.out_y1 = std::min(g.valid_y1, g.out_y1 + (kh - 1 - ry));
+    g1.dst_y0 = g1.out_y0;
+    rc = stencil_convolve(ctx, src, aux, krow, kw, 1, g1, nullptr);
+    if (rc == DIP_OK) rc = stencil_convolve(ctx, aux, dst, kcol, 1, kh, g, nullptr);
+    dip_image_destroy(aux);
+    return rc;
 }
 
 int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps) {
@@ -533,6 +567,7 @@ int dip_debug_set(const char* key, int value) {
     if (!key) return fail(nullptr, DIP_ERR_ARG, "null key");
     if (!strcmp(key, "tile_rows")) g_knobs.tile_rows = value;
     else if (!strcmp(key, "int_math")) g_knobs.int_math = value;
+    else if (!strcmp(key, "direct_generic")) g_knobs.direct_generic = value;
     else if (!strcmp(key, "no_pad")) g_no_occupancy_pad = value != 0;
     else return fail(nullptr, DIP_ERR_ARG, "unknown knob %s", key);
     return DIP_OK;

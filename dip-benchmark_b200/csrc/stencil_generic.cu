@@ -1,0 +1,223 @@
+// Tiled kernels for ARBITRARY small masks / kernels (up to 7 x 7): SURVEY.md 8f rank 3 -- the reference's operations
+// take the mask / kernel as a runtime argument (sycl/benchmark.cpp:123,166, visiongl:125-131) even though the benchmark
+// passes only seven fixed ones, which have kernels of their own (stencil.cu).
+//
+// Same frame as those: one TMA tile (512 bytes + 16-byte halo, 32 rows + kh/2 halo rows) per CTA, borders patched in
+// shared memory, a thread owns a 16-byte column of 8 rows.  The taps travel by value in the kernel parameters (the
+// constant bank), not through global memory as the reference's do.  The arithmetic is generic: for every tap row the
+// thread converts the 16 + 2*RX*C bytes it needs to fp32 once (PRMT into the mantissa of 2^23, one FADD) and runs
+// (2*RX+1) x 16 FFMAs (convolution: fp32 accumulation in row-major tap order, cvRound, saturate -- bit-exact for
+// dyadic kernels, within 1 LSB otherwise, like the direct kernel in stencil.cu) or FMNMXs (erosion / dilation; the
+// bytes are exact in fp32).  Larger masks keep the direct kernel.
+#include "stencil_tiled.cuh"
+
+namespace dip {
+
+namespace {
+
+constexpr int kGenWarps = 4, kGenRows = 8, kGenTH = kGenWarps * kGenRows;
+
+// reflect-101 / constant border patch with runtime radii (the tiled kernels' patch_borders has them as template constants)
+template <int C, int kThreads>
+__device__ void patch_borders_rt(uint8_t* tile, const StencilParams& p, int bx0, int ytop, int rx, int ry, int rows, bool morph, uint8_t fill) {
+    const int tid = threadIdx.x;
+    const bool left = rx > 0 && bx0 <= 0;
+    const bool right = rx > 0 && bx0 + kTileBytes + rx * C > p.rowbytes;
+    if (left || right) {
+        const int per_row = 2 * rx * C;
+        for (int i = tid; i < rows * per_row; i += kThreads) {
+            const int t = i / per_row;
+            int k = i - t * per_row;
+            const int y = ytop + t;
+            if (y < p.valid_y0 || y >= p.valid_y1) continue;
+            const bool is_right = k >= rx * C;
+            if (is_right) k -= rx * C;
+            const int d = k / C, ch = k - d * C;
+            if (is_right ? !right : !left) continue;
+            const int px = is_right ? p.width + d : -1 - d;
+            const int lb = px * C + ch - (bx0 - kHalo);
+            if (lb < 0 || lb >= kRowBytes) continue;
+            uint8_t v = fill;
+            if (!morph) {
+                const int sb = reflect101(px, p.width) * C + ch - (bx0 - kHalo);
+                v = (sb >= 0 && sb < kRowBytes) ? tile[t * kRowBytes + sb] : 0;  // a reflected source outside this tile: rows narrower than the radius
+            }
+            tile[t * kRowBytes + lb] = v;
+        }
+        __syncthreads();
+    }
+    const bool top = ry > 0 && ytop < p.valid_y0;
+    const bool bottom = ry > 0 && ytop + rows > p.valid_y1;
+    if (top || bottom) {
+        constexpr int vec_per_row = kRowBytes / 16;
+        for (int i = tid; i < rows * vec_per_row; i += kThreads) {
+            const int t = i / vec_per_row, vx = i - t * vec_per_row;
+            const int y = ytop + t;
+            if (y >= p.valid_y0 && y < p.valid_y1) continue;
+            if (y < p.valid_y0 - ry || y >= p.valid_y1 + ry) continue;
+            uint4 v = make_uint4(fill * 0x01010101u, fill * 0x01010101u, fill * 0x01010101u, fill * 0x01010101u);
+            if (!morph) {
+                const int ts = p.valid_y0 + reflect101(y - p.valid_y0, p.valid_y1 - p.valid_y0) - ytop;
+                if (ts < 0 || ts >= rows) continue;
+                v = *reinterpret_cast<const uint4*>(tile + ts * kRowBytes + vx * 16);
+            }
+            *reinterpret_cast<uint4*>(tile + t * kRowBytes + vx * 16) = v;
+        }
+        __syncthreads();
+    }
+}
+
+// byte `B` of the 12-word window (word 4 = the thread's first own word) as fp32
+template <int B>
+__device__ __forceinline__ float win_byte(const uint32_t (&w)[12]) {
+    static_assert(B >= 0 && B < 48, "window");
+    return __uint_as_float(__byte_perm(w[B / 4], 0x4B000000u, 0x7650 + (B & 3))) - 8388608.0f;
+}
+
+template <int MODE, int C, int RX, int N, int I = 0>
+struct RowTaps {
+    // acc[b] (op)= wt[k] * f[b + k*C] for every tap column k and own byte b; f[q] = window byte 16 - RX*C + q
+    static __device__ __forceinline__ void fill(const uint32_t (&w)[12], float (&f)[N]) {
+        if constexpr (I < N) {
+            f[I] = win_byte<16 - RX * C + I>(w);
+            RowTaps<MODE, C, RX, N, I + 1>::fill(w, f);
+        }
+    }
+};
+
+template <int MODE, int C, int RX>  // MODE 0 erode, 1 dilate, 2 correlation
+__global__ void __launch_bounds__(kGenWarps * 32) generic_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p, const SmallTaps taps) {
+    constexpr int kThreads = kGenWarps * 32;
+    constexpr int N = 16 + 2 * RX * C;   // bytes of a tap row one thread reads
+    static_assert(RX * C <= 16, "horizontal reach beyond the 16-byte halo");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int ry = taps.kh / 2;
+    const int rows = kGenTH + 2 * ry;
+    uint8_t* tile = smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + rows * kRowBytes);
+    const int tx = blockIdx.x, ty = blockIdx.y, f = blockIdx.z;
+    const int bx0 = tx * kTileBytes;
+    const int y0 = p.out_y0 + ty * kGenTH;
+    const int ytop = y0 - ry;
+
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar, rows * kRowBytes);
+    }
+    pdl_wait();
+    if (threadIdx.x == 0) tma_load_3d(tile, &tmap, bar, (bx0 - kHalo) / 4, ytop, f);
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const bool border = bx0 == 0 || bx0 + kTileBytes + RX * C > p.rowbytes || ytop < p.valid_y0 || ytop + rows > p.valid_y1;
+    if (border) {
+        __syncthreads();
+        patch_borders_rt<C, kThreads>(tile, p, bx0, ytop, RX, ry, rows, MODE != 2, MODE == 1 ? 0 : 255);
+    }
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cx = bx0 + 16 * lane;
+    const int yw = y0 + warp * kGenRows;
+    if (cx >= ((p.rowbytes + 15) & ~15) || yw >= p.out_y1) return;
+    const int nrows = min(kGenRows, p.out_y1 - yw);
+    const uint8_t* colp = tile + (warp * kGenRows) * kRowBytes + kHalo + 16 * lane;  // tile row of source row yw - ry
+    uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
+    const int valid = p.dst_exact ? min(16, p.rowbytes - cx) : 16;
+
+    for (int i = 0; i < nrows; ++i) {
+        float acc[16];
+#pragma unroll
+        for (int b = 0; b < 16; ++b) acc[b] = MODE == 0 ? 255.0f : 0.0f;
+        for (int dy = 0; dy < taps.kh; ++dy) {
+            const uint8_t* rp = colp + (i + dy) * kRowBytes;
+            const uint4 wa = *reinterpret_cast<const uint4*>(rp - 16);
+            const uint4 wb = *reinterpret_cast<const uint4*>(rp);
+            const uint4 wc = *reinterpret_cast<const uint4*>(rp + 16);
+            const uint32_t w[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+            float fw[N];
+            RowTaps<MODE, C, RX, N>::fill(w, fw);
+#pragma unroll
+            for (int k = 0; k <= 2 * RX; ++k) {
+                const float wt = taps.w[dy][k];
+                if (MODE == 2) {
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) acc[b] = __fmaf_rn(wt, fw[b + k * C], acc[b]);
+                } else if (wt != 0.0f) {   // uniform: is this position of the mask set?
+#pragma unroll
+                    for (int b = 0; b < 16; ++b) acc[b] = MODE == 0 ? fminf(acc[b], fw[b + k * C]) : fmaxf(acc[b], fw[b + k * C]);
+                }
+            }
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                const int r = MODE == 2 ? min(max(__float2int_rn(acc[4 * j + b]), 0), 255) : (int)acc[4 * j + b];  // cvRound + saturate_cast<uchar>
+                word |= (uint32_t)r << (8 * b);
+            }
+            o[j] = word;
+        }
+        store16(dptr + (size_t)i * p.dst.pitch, make_uint4(o[0], o[1], o[2], o[3]), valid);
+    }
+}
+
+template <int MODE, int C, int RX>
+int launch_generic_tiled_t(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
+    const int rows = kGenTH + 2 * (taps.kh / 2);
+    const int smem_bytes = rows * kRowBytes + 16;
+    const CUtensorMap* map = nullptr;
+    int rc = get_tmap(ctx, const_cast<dip_image*>(src), kBoxWords, rows, &map);
+    if (rc != DIP_OK) return rc;
+    StencilParams p{};
+    p.dst = dst->v;
+    p.rowbytes = src->v.rowbytes;
+    p.width = src->v.width;
+    p.valid_y0 = g.valid_y0; p.valid_y1 = g.valid_y1;
+    p.out_y0 = g.out_y0; p.out_y1 = g.out_y1; p.dst_y0 = g.dst_y0;
+    p.tiles_x = (src->v.rowbytes + kTileBytes - 1) / kTileBytes;
+    p.tiles_y = (g.out_y1 - g.out_y0 + kGenTH - 1) / kGenTH;
+    p.dst_exact = exact_rows(dst->v);
+    if (p.tiles_x <= 0 || p.tiles_y <= 0) return DIP_OK;
+    if (p.tiles_y > 65535 || src->v.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
+    DIP_CUDA(ctx, launch_kernel(generic_tiled_kernel<MODE, C, RX>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
+                                dim3(kGenWarps * 32), smem_bytes, ctx->compute, *map, p, taps));
+    DIP_CHECK_LAUNCH(ctx, "generic_tiled_kernel");
+    return DIP_OK;
+}
+
+template <int MODE, int C>
+int launch_generic_tiled_c(dip_ctx* ctx, int rx, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
+    switch (rx) {
+        case 1: return launch_generic_tiled_t<MODE, C, 1>(ctx, src, dst, g, taps);
+        case 2: return launch_generic_tiled_t<MODE, C, 2>(ctx, src, dst, g, taps);
+        case 3: return launch_generic_tiled_t<MODE, C, 3>(ctx, src, dst, g, taps);
+    }
+    return fail(ctx, DIP_ERR_ARG, "bad horizontal radius %d", rx);
+}
+
+template <int MODE>
+int launch_generic_tiled_m(dip_ctx* ctx, int rx, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
+    switch (src->v.channels) {
+        case 1: return launch_generic_tiled_c<MODE, 1>(ctx, rx, src, dst, g, taps);
+        case 3: return launch_generic_tiled_c<MODE, 3>(ctx, rx, src, dst, g, taps);
+        case 4: return launch_generic_tiled_c<MODE, 4>(ctx, rx, src, dst, g, taps);
+    }
+    return fail(ctx, DIP_ERR_ARG, "bad channel count");
+}
+
+}  // namespace
+
+int launch_generic_tiled(dip_ctx* ctx, int mode, int kw, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
+    const int rx = std::max(1, kw / 2);
+    switch (mode) {
+        case 0: return launch_generic_tiled_m<0>(ctx, rx, src, dst, g, taps);
+        case 1: return launch_generic_tiled_m<1>(ctx, rx, src, dst, g, taps);
+        case 2: return launch_generic_tiled_m<2>(ctx, rx, src, dst, g, taps);
+    }
+    return fail(ctx, DIP_ERR_ARG, "bad mode");
+}
+
+}  // namespace dip

@@ -24,6 +24,11 @@
  *    SYCL backend waits after every call, sycl:335; dip_sync() gives that).
  *  - one dip_ctx per (host thread, GPU); a ctx is not thread-safe.
  *  - there is no CPU fallback: without a CUDA device dip_init fails.
+ *  - pixel type: 8-bit unsigned only, like every backend of the reference (cv.imread's CV_8U, sycl uint8_t*).
+ *    16-bit images (last item) are NOT implemented: there is no entry point that takes them, and
+ *    wrapping 16-bit memory as twice as many 8-bit columns gives the 8-bit result of those bytes, not a 16-bit one.
+ *  - masks / kernels: the benchmark's seven run on dedicated kernels; any other mask / kernel of up to 7 x 7 taps on a
+ *    tiled generic kernel, up to 15 x 15 (225 taps) on a direct one; larger ones return DIP_ERR_UNSUPPORTED.
  */
 #ifndef DIP_H_
 #define DIP_H_
@@ -150,7 +155,8 @@ DIP_API int dip_convolve(dip_ctx* ctx, const dip_image* src, dip_image* dst, con
                          int kw, int kh);
 /* "Convolution (1xK+Kx1)": convolution_*_separated opencv:84-90,:102,:104, sycl:347-356 --
  * row pass (1 x kw) rounded to u8 exactly as the reference's `aux` image is, then column
- * pass (kh x 1), fused in one kernel. */
+ * pass (kh x 1).  The benchmark's binomial pairs ([1 2 1]/4, [1 4 6 4 1]/16) are ONE fused kernel; any other pair
+ * runs as the reference's two calls, with a scratch stack owned by the ctx as `aux` (allocated on first use). */
 DIP_API int dip_convolve_separable(dip_ctx* ctx, const dip_image* src, dip_image* dst,
                                    const float* krow, int kw, const float* kcol, int kh);
 /* "Gaussian Blur (3x3)": cv.GaussianBlur(image,(3,3),0) opencv:105,

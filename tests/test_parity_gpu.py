@@ -886,3 +886,95 @@ def test_chain_host_pipeline(ctx, dip, orc):
     pin_out = ctx.pinned_empty(stack.shape); pin_out[...] = 0
     ctx.run_chain_host(pin_in, ops, pin_out, chunk_frames=2)
     assert np.array_equal(pin_out, want)
+
+
+def test_arbitrary_small_masks_kernels_and_separable_pairs(ctx, dip, orc):
+    """masks / kernels as runtime arguments (sycl/benchmark.cpp:123,166).  Anything up to 7 x 7 that is
+    not one of the benchmark's seven runs on the tiled generic kernel (stencil_generic.cu); any pair of row / column
+    kernels runs as the reference's two calls through `aux` (dip_convolve_separable no longer rejects them).  Dyadic
+    weights are bit-exact against the oracle, others within 1 LSB; the direct kernel (knob) gives the same bits."""
+    rng = np.random.default_rng(77)
+    L = dip.lib()
+    for trial in range(40):
+        c = int(rng.choice([1, 3, 4]))
+        h, w = int(rng.integers(1, 90)), int(rng.integers(1, 700))
+        img = rand_img(rng, h, w, c)
+        kw, kh = int(rng.integers(1, 8)), int(rng.integers(1, 8))
+        mask = (rng.random((kh, kw)) < 0.6).astype(np.uint8)
+        if not mask.any():
+            mask[kh // 2, kw // 2] = 1
+        dyadic = trial % 2 == 0
+        if dyadic:
+            kern = rng.integers(-8, 24, (kh, kw)).astype(np.float32) / 64.0   # exact in fp32 whatever the order; saturates sometimes
+        else:
+            kern = rng.random((kh, kw)).astype(np.float32)
+            kern /= kern.sum()
+        got_e, got_d = run_op(ctx, "erode", (mask,), img), run_op(ctx, "dilate", (mask,), img)
+        assert np.array_equal(got_e, orc.erode(img, mask)), (trial, "erode", mask.shape, c)
+        assert np.array_equal(got_d, orc.dilate(img, mask)), (trial, "dilate", mask.shape, c)
+        got_c = run_op(ctx, "convolve", (kern,), img)
+        diff = np.abs(got_c.astype(int) - orc.filter2d(img, kern).astype(int)).max()
+        assert diff <= (0 if dyadic else 1), (trial, "convolve", kern.shape, c, diff)
+        L.dip_debug_set(b"direct_generic", 1)
+        try:
+            assert np.array_equal(run_op(ctx, "erode", (mask,), img), got_e)
+            assert np.array_equal(run_op(ctx, "convolve", (kern,), img), got_c), (trial, "direct vs tiled")
+        finally:
+            L.dip_debug_set(b"direct_generic", 0)
+        # separable pair: row kernel then column kernel with the u8 intermediate of the reference's `aux` image
+        krow = (rng.integers(0, 16, kw).astype(np.float32) / 32.0) if dyadic else rng.random(kw).astype(np.float32) / kw * 1.5
+        kcol = (rng.integers(0, 16, kh).astype(np.float32) / 32.0) if dyadic else rng.random(kh).astype(np.float32) / kh * 1.5
+        got_s = run_op(ctx, "convolve_separable", (krow, kcol), img)
+        want_s = orc.filter2d_separable(img, krow[None, :], kcol[:, None])
+        diff = np.abs(got_s.astype(int) - want_s.astype(int)).max()
+        assert diff <= (0 if dyadic else 2), (trial, "separable", kw, kh, c, diff)   # two roundings: a 1-LSB intermediate can move the result by 1 more
+    # stacks and row bands go through the same kernels
+    stack = rng.integers(0, 256, (3, 50, 301, 3), dtype=np.uint8)
+    kern = rng.integers(0, 9, (5, 7)).astype(np.float32) / 128.0
+    got = run_op(ctx, "convolve", (kern,), stack)
+    for f in range(3):
+        assert np.array_equal(got[f], orc.filter2d(stack[f], kern))
+
+
+def test_graph_replay_of_the_operation_list(ctx, dip, orc):
+    """dip_graph_begin / end / launch: the 12 reference operations (and a fused chain) recorded once, replayed twice on new
+    input contents; transfers and syncs are refused while recording."""
+    rng = np.random.default_rng(8)
+    img = rng.integers(0, 256, (2, 80, 333, 3), dtype=np.uint8)
+    src = ctx.from_array(img)
+    outs = [ctx.image_like(src) for _ in dip.REFERENCE_OPS]
+    chain_out = ctx.image_like(src)
+    ops = {p: op for _, p, op in ctx.reference_ops()}
+    chain = [ops["grayscale"], ops["gaussian-blur-3x3"], ops["threshold"], ops["erosion-cross"]]
+    ctx.apply_chain(chain, src, chain_out)   # allocates the chain's scratch stack (cannot happen while recording)
+    ctx.sync()
+    before = ctx.launch_count()
+    ctx.graph_begin()
+    for (prefix, name, args), o in zip(dip.REFERENCE_OPS, outs):
+        getattr(ctx, name)(src, o, *args)
+    ctx.apply_chain(chain, src, chain_out)
+    with pytest.raises(dip.DipError):
+        src.upload(img)
+    with pytest.raises(dip.DipError):
+        ctx.sync()
+    g = ctx.graph_end()
+    assert ctx.launch_count() == before          # recorded, not run
+    for rep in range(2):
+        img2 = rng.integers(0, 256, img.shape, dtype=np.uint8)
+        src.upload(img2)
+        ctx.sync()
+        g.launch()
+        for (prefix, _, _), (_, ofn), o in zip(dip.REFERENCE_OPS, orc.OPERATIONS, outs):
+            got = o.download()
+            for f in range(2):
+                assert np.array_equal(got[f], ofn(img2[f])), (rep, prefix)
+        want = img2
+        got = chain_out.download()
+        for f in range(2):
+            w = orc.erode(orc.threshold(orc.gaussian_blur3x3(orc.grayscale(img2[f])), 127, 255), orc.CROSS_MASK)
+            assert np.array_equal(got[f], w), rep
+    assert ctx.launch_count() - before == 2 * (12 + 3)   # the chain is three passes
+    g.close()
+    src.close(); chain_out.close()
+    for o in outs:
+        o.close()
