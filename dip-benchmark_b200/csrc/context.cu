@@ -58,11 +58,48 @@ int begin_op(dip_ctx* ctx, const dip_image* src, dip_image* dst) {
     for (dip_image* im : imgs) {
         if (im && im->copy_pending) {
             // dip_graph_begin synchronised the copy streams, so a pending flag here is only stale bookkeeping
+            dep_touch(ctx);
             if (!ctx->capturing) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, im->copy_done, 0));
             im->copy_pending = false;
         }
     }
     return DIP_OK;
+}
+
+static bool dep_conflict(const std::vector<DepRange>& set, const DepRange* r, int n) {
+    for (const DepRange& a : set)
+        for (int i = 0; i < n; ++i)
+            if ((a.write || r[i].write) && a.lo < r[i].hi && r[i].lo < a.hi) return true;
+    return false;
+}
+
+LaunchMode plan_launch(dip_ctx* ctx, const DepRange* ranges, int n) {
+    DepTracker& d = ctx->dep;
+    static const DepRange everything{0, ~(uintptr_t)0, true};
+    if (n <= 0) { ranges = &everything; n = 1; }
+    const bool touched = d.touched;
+    d.touched = false;
+    // inside a graph recording the stream's in-order completion does not exist (edges are per node): always wait
+    const bool may_skip = pdl_enabled() && !ctx->capturing && !touched && !d.guaranteed.empty();
+    constexpr size_t kCap = 24;   // a full launch now and then keeps the sets (and the search) small
+    if (d.guaranteed.size() + d.unsafe.size() + (size_t)n <= kCap && !dep_conflict(d.unsafe, ranges, n)) {
+        if (may_skip && !dep_conflict(d.guaranteed, ranges, n)) {
+            // independent of everything that may still run: no wait.  Waiting on THIS kernel later proves nothing about
+            // the ones before it, so they are no longer implied by "the last kernel has finished".
+            d.unsafe.insert(d.unsafe.end(), d.guaranteed.begin(), d.guaranteed.end());
+            d.guaranteed.assign(ranges, ranges + n);
+            return kNoWait;
+        }
+        // depends (at most) on kernels whose completion the previous kernel's completion implies: the usual
+        // programmatic wait; this kernel's completion then implies theirs too
+        d.guaranteed.insert(d.guaranteed.end(), ranges, ranges + n);
+        return kPdlWait;
+    }
+    // depends on a kernel that a wait on the previous one would not cover (or the sets are full): an ordinary launch,
+    // which starts after everything before it in the stream has finished
+    d.unsafe.clear();
+    d.guaranteed.assign(ranges, ranges + n);
+    return kFull;
 }
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -261,6 +298,9 @@ int dip_sync(dip_ctx* ctx) {
     DIP_CUDA(ctx, cudaStreamSynchronize(ctx->halo));
     DIP_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     DIP_CUDA(ctx, cudaStreamSynchronize(ctx->download));
+    ctx->dep.unsafe.clear();
+    ctx->dep.guaranteed.clear();
+    ctx->dep.touched = true;
     return DIP_OK;
 }
 
@@ -546,6 +586,7 @@ int dip_upload(dip_ctx* ctx, dip_image* dst_view, const uint8_t* host, size_t ho
     if (host_pitch == 0) host_pitch = rowb;
     if (host_pitch < rowb) return fail(ctx, DIP_ERR_ARG, "host pitch %zu < row bytes %zu", host_pitch, rowb);
     // the copy must not overtake kernels still reading/writing dst
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->compute));
     DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->upload, ctx->ev_compute, 0));
     if (dst->copy_pending) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->upload, dst->copy_done, 0));
@@ -566,6 +607,7 @@ int dip_download(dip_ctx* ctx, const dip_image* src_c, uint8_t* host, size_t hos
     const size_t rowb = (size_t)v.rowbytes;
     if (host_pitch == 0) host_pitch = rowb;
     if (host_pitch < rowb) return fail(ctx, DIP_ERR_ARG, "host pitch %zu < row bytes %zu", host_pitch, rowb);
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->compute));
     DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->download, ctx->ev_compute, 0));
     if (src->copy_pending) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->download, src->copy_done, 0));
@@ -589,6 +631,7 @@ int dip_graph_begin(dip_ctx* ctx) {
     if (ctx->capturing) return fail(ctx, DIP_ERR_ARG, "a graph is already being recorded on this ctx");
     int rc = dip_sync(ctx);  // outstanding transfers finish now: a recording cannot wait for work outside itself
     if (rc != DIP_OK) return rc;
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaStreamBeginCapture(ctx->compute, cudaStreamCaptureModeThreadLocal));
     ctx->capturing = true;
     ctx->capture_launches0 = ctx->launches;
@@ -600,6 +643,9 @@ int dip_graph_end(dip_ctx* ctx, dip_graph** out) {
     *out = nullptr;
     if (!ctx->capturing) return fail(ctx, DIP_ERR_ARG, "dip_graph_begin was not called");
     ctx->capturing = false;
+    dep_touch(ctx);
+    ctx->dep.unsafe.clear();
+    ctx->dep.guaranteed.clear();   // what was recorded did not run
     cudaGraph_t graph = nullptr;
     cudaError_t e = cudaStreamEndCapture(ctx->compute, &graph);
     if (e != cudaSuccess || !graph) { cudaGetLastError(); return fail(ctx, DIP_ERR_CUDA, "recording failed: %s (transfers, dip_sync and first-time allocations cannot be recorded)", cudaGetErrorString(e)); }
@@ -619,6 +665,7 @@ int dip_graph_launch(dip_ctx* ctx, dip_graph* g) {
     if (!ctx || !g || g->ctx != ctx) return fail(ctx, DIP_ERR_ARG, "bad graph");
     if (ctx->capturing) return fail(ctx, DIP_ERR_ARG, "cannot replay a graph while recording");
     DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaGraphLaunch(g->exec, ctx->compute));
     ctx->launches += g->kernels;
     return DIP_OK;
@@ -635,12 +682,14 @@ int dip_graph_destroy(dip_graph* g) {
 // ---- timing, counters, L2 flush ---------------------------------------------------------
 int dip_timer_start(dip_ctx* ctx) {
     if (!ctx) return fail(nullptr, DIP_ERR_ARG, "ctx is null");
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaEventRecord(ctx->t0, ctx->compute));
     return DIP_OK;
 }
 
 int dip_timer_stop(dip_ctx* ctx, float* ms) {
     if (!ctx || !ms) return fail(ctx, DIP_ERR_ARG, "null argument");
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaEventRecord(ctx->t1, ctx->compute));
     DIP_CUDA(ctx, cudaEventSynchronize(ctx->t1));
     DIP_CUDA(ctx, cudaEventElapsedTime(ms, ctx->t0, ctx->t1));
@@ -654,6 +703,7 @@ int dip_mark(dip_ctx* ctx, int slot) {
         DIP_CUDA(ctx, cudaEventCreate(&e));
         ctx->marks.push_back(e);
     }
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaEventRecord(ctx->marks[slot], ctx->compute));
     return DIP_OK;
 }
@@ -693,9 +743,11 @@ int dip_checksum_rows(dip_ctx* ctx, const dip_image* img, uint64_t first_row, ui
         DIP_CUDA(ctx, cudaMalloc(&ctx->d_checksums, sizeof(uint64_t) * (size_t)n));
         ctx->d_checksums_cap = n;
     }
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaMemsetAsync(ctx->d_checksums, 0, sizeof(uint64_t) * (size_t)n, ctx->compute));
     rc = launch_checksum(ctx, img->v, first_row, ctx->d_checksums);
     if (rc != DIP_OK) return rc;
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaMemcpyAsync(per_frame, ctx->d_checksums, sizeof(uint64_t) * (size_t)n, cudaMemcpyDeviceToHost, ctx->compute));
     DIP_CUDA(ctx, cudaStreamSynchronize(ctx->compute));
     return DIP_OK;
@@ -753,6 +805,7 @@ int dip_copy_rows(dip_ctx* ctx, const dip_image* src, int src_row, dip_image* ds
         return fail(ctx, DIP_ERR_ARG, "row range out of bounds");
     DIP_CUDA(ctx, cudaSetDevice(ctx->device));
     // ordered after everything enqueued on the compute stream so far
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaEventRecord(ctx->ev_compute, ctx->compute));
     DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->halo, ctx->ev_compute, 0));
     for (int f = 0; f < a.frames; ++f)
@@ -815,6 +868,7 @@ int dip_flag_signal(dip_ctx* ctx, dip_image* flags, int index, uint32_t value) {
     int rc = flag_word(ctx, flags, index, &word);
     if (rc != DIP_OK) return rc;
     DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    dep_touch(ctx);
     flag_signal_kernel<<<1, 1, 0, ctx->compute>>>(word, value);  // plain launch: runs after every earlier kernel of the stream has finished
     DIP_CHECK_LAUNCH(ctx, "flag_signal_kernel");
     return DIP_OK;
@@ -828,6 +882,7 @@ int dip_flag_wait(dip_ctx* ctx, const dip_image* flags, int index, uint32_t valu
     PFN_streamWaitValue32 fn = stream_wait_value_fn();
     if (!fn) return fail(ctx, DIP_ERR_UNSUPPORTED, "cuStreamWaitValue32 is not available from the driver");
     DIP_CUDA(ctx, cudaSetDevice(ctx->device));
+    dep_touch(ctx);
     const CUresult r = fn(reinterpret_cast<CUstream>(ctx->compute), reinterpret_cast<CUdeviceptr>(word), value, 0x0 /* CU_STREAM_WAIT_VALUE_GEQ */);
     if (r != CUDA_SUCCESS) return fail(ctx, DIP_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", (int)r);
     return DIP_OK;
@@ -846,6 +901,7 @@ int dip_flag_read(dip_ctx* ctx, const dip_image* flags, int index, uint32_t* val
 int dip_halo_fence(dip_ctx* ctx) {
     if (!ctx) return fail(nullptr, DIP_ERR_ARG, "ctx is null");
     DIP_CUDA(ctx, cudaEventRecord(ctx->ev_halo, ctx->halo));
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, ctx->ev_halo, 0));
     return DIP_OK;
 }

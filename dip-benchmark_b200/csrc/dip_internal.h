@@ -56,6 +56,32 @@ struct dip_image {
     std::vector<dip::TmapKey> tmaps;  // cached TMA descriptors of this allocation's views (used on the root image only)
 };
 
+namespace dip {
+
+// Which earlier kernels of the compute stream may still be running when the next one starts, and what they touch.
+// Every kernel is launched with programmatic stream serialization, so its CTAs may start while its predecessor still
+// runs; a kernel that depends on earlier work executes griddepcontrol.wait first (kPdlWait).  An operation whose source
+// and destination do not overlap anything an unfinished kernel touches skips that wait (kNoWait): consecutive
+// independent calls -- the reference's loop over a ring of images, a batch driver walking its frames -- then overlap
+// the tail of one kernel with the ramp of the next (one 3504x2336 image: 8.8 -> 7.2 us for a point op, 15.9 -> 10 us
+// for the fused 1x5+5x1 Gaussian).  tools/ubench/pdl_order.cu checks what this relies on: whatever follows a no-wait
+// kernel in the stream (an event record, a copy, a normally launched kernel, a synchronize) completes only after ALL
+// earlier kernels have.
+//   guaranteed: possibly running when the next kernel starts, but complete once the LAST launched kernel is (it, and
+//               whatever it waited for, transitively)
+//   unsafe:     possibly running and NOT implied by the last kernel's completion (launched before a no-wait kernel)
+enum LaunchMode { kPdlWait = 0, kNoWait = 1, kFull = 2 };
+struct DepRange {
+    uintptr_t lo, hi;   // [lo, hi) device bytes
+    bool write;
+};
+struct DepTracker {
+    std::vector<DepRange> guaranteed, unsafe;
+    bool touched = true;   // something other than a tracked kernel launch was enqueued on the compute stream since
+};
+
+}  // namespace dip
+
 struct dip_graph {
     dip_ctx* ctx = nullptr;
     cudaGraph_t graph = nullptr;
@@ -92,6 +118,7 @@ struct dip_ctx {
     // library-owned intermediate stacks (grown on shape change): [0] dip_apply_chain's ping-pong partner, [1] the `aux`
     // image of the two-pass separable convolution (a chain may run such a convolution between its own two buffers)
     dip_image* scratch[2] = {nullptr, nullptr};
+    dip::DepTracker dep;
     bool capturing = false;              // between dip_graph_begin and dip_graph_end: kernels are recorded, not run
     uint64_t capture_launches0 = 0;
     std::string last_error;
@@ -126,8 +153,22 @@ inline bool pdl_enabled() {
     return on;
 }
 
+// ranges = what the kernel reads / writes (n == 0: unknown, treated as everything).  Returns how to launch it and
+// updates the tracker; the caller passes `mode != kNoWait` to the kernel as its wait flag.
+LaunchMode plan_launch(dip_ctx* ctx, const DepRange* ranges, int n);
+// a non-kernel operation is about to be enqueued on the compute stream (event, wait, copy, memset, graph launch)
+inline void dep_touch(dip_ctx* ctx) { ctx->dep.touched = true; }
+inline DepRange dep_range(const ImgView& v, bool write) {
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(v.base);
+    return DepRange{lo, lo + v.frame_stride * (size_t)(v.frames - 1) + v.pitch * (size_t)v.height, write};
+}
+inline LaunchMode plan_launch(dip_ctx* ctx, const ImgView& src, const ImgView& dst) {
+    const DepRange r[2] = {dep_range(src, false), dep_range(dst, true)};
+    return plan_launch(ctx, r, 2);
+}
+
 template <typename... KArgs, typename... Args>
-cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+cudaError_t launch_kernel(LaunchMode mode, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = grid;
     cfg.blockDim = block;
@@ -137,7 +178,7 @@ cudaError_t launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    cfg.numAttrs = (pdl_enabled() && mode != kFull) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
@@ -216,6 +257,8 @@ __device__ __forceinline__ uint4 map_vec(uint4 v, const MapParams& m) {
 
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// `wait` = false: the host proved this launch independent of every kernel that may still be running (plan_launch)
+__device__ __forceinline__ void pdl_wait(bool wait) { if (wait) asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
 
 // Make the compute stream wait for outstanding copies on the operands, and set the device.
@@ -237,6 +280,7 @@ int launch_point_chain(dip_ctx* ctx, const ImgView& src, const ImgView& dst, con
 int launch_synth(dip_ctx* ctx, const ImgView& dst, uint32_t seed, uint64_t first_row);
 int launch_checksum(dip_ctx* ctx, const ImgView& src, uint64_t first_row, uint64_t* d_out);
 int launch_fill(dip_ctx* ctx, uint8_t* p, size_t bytes, uint32_t value);
+
 
 // ---- stencils (stencil.cu) ------------------------------------------------------------
 // Row geometry of a stencil launch.  The source's rows [valid_y0, valid_y1) are the image

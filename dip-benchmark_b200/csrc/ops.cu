@@ -215,6 +215,7 @@ int dip::scratch_view(dip_ctx* ctx, int slot, const dip_image* like, dip_image**
     if (!(s && s->v.width == like->v.width && s->v.height == like->v.height && s->v.channels == like->v.channels && s->v.frames >= like->v.frames)) {
         if (ctx->capturing) return fail(ctx, DIP_ERR_UNSUPPORTED, "run this chain once before recording it: its scratch stack is allocated on first use");
         if (s) {
+            dep_touch(ctx);
             DIP_CUDA(ctx, cudaStreamSynchronize(ctx->compute));  // kernels may still be reading the old one
             dip_image_destroy(s);
             ctx->scratch[slot] = nullptr;
@@ -482,6 +483,7 @@ int dip_pipeline_run(dip_pipeline* p, const uint8_t* host_in, int in_ring, int f
         if (rc == DIP_OK) rc = enqueue_upload(ctx, iv->v, host_in + frame_bytes * (size_t)(f0 % in_ring), frame_bytes / p->h);
         if (rc == DIP_OK) {
             cu(cudaEventRecord(p->in_ready[slot], ctx->upload), "cudaEventRecord(in_ready)");
+            dep_touch(ctx);
             cu(cudaStreamWaitEvent(ctx->compute, p->in_ready[slot], 0), "cudaStreamWaitEvent(compute, in_ready)");
         }
         for (int o = 0; o < p->n_out && rc == DIP_OK; ++o) {
@@ -489,9 +491,11 @@ int dip_pipeline_run(dip_pipeline* p, const uint8_t* host_in, int in_ring, int f
             dip_image* ov = nullptr;
             if ((rc = dip_image_view(ctx, p->out[idx], 0, n, &ov)) != DIP_OK) break;
             // the kernel may overwrite this output slot only after its previous download finished
+            dep_touch(ctx);
             if (used[slot]) cu(cudaStreamWaitEvent(ctx->compute, p->out_free[idx], 0), "cudaStreamWaitEvent(compute, out_free)");
             if (rc == DIP_OK) rc = p->chain ? dip_apply_chain(ctx, p->ops.data(), p->n_ops, iv, ov) : dip_apply(ctx, &p->ops[o], iv, ov);
             if (rc == DIP_OK) {
+                dep_touch(ctx);
                 cu(cudaEventRecord(p->out_ready[idx], ctx->compute), "cudaEventRecord(out_ready)");
                 cu(cudaStreamWaitEvent(ctx->download, p->out_ready[idx], 0), "cudaStreamWaitEvent(download, out_ready)");
                 bool completed = false;
@@ -500,6 +504,7 @@ int dip_pipeline_run(dip_pipeline* p, const uint8_t* host_in, int in_ring, int f
             }
             dip_image_destroy(ov);
         }
+        dep_touch(ctx);
         if (rc == DIP_OK) cu(cudaEventRecord(p->in_free[slot], ctx->compute), "cudaEventRecord(in_free)");
         used[slot] = true;
         dip_image_destroy(iv);

@@ -70,9 +70,9 @@ __device__ __forceinline__ uint4 point_vec(uint4 v, const MapParams& m, const Ma
 template <int OP, int UNROLL>
 __global__ void __launch_bounds__(kThreads) point_flat_kernel(const uint4* __restrict__ src,
                                                               uint4* __restrict__ dst, size_t nvec,
-                                                              const MapParams m, const MapParams post) {
+                                                              const MapParams m, const MapParams post, const bool wait_prev) {
     pdl_launch_dependents();
-    pdl_wait();
+    pdl_wait(wait_prev);
     const size_t base = (size_t)blockIdx.x * (kThreads * UNROLL) + threadIdx.x;
     uint4 v[UNROLL];
     if (base + (size_t)(UNROLL - 1) * kThreads < nvec) {
@@ -182,10 +182,10 @@ __global__ void __launch_bounds__(kThreads) gray3_kernel(ImgView src, ImgView ds
 // shared memory at a 48-byte stride (12 banks apart: conflict-free for 128-bit accesses).
 template <bool MAPPED>
 __global__ void __launch_bounds__(kThreads) gray3_flat_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, size_t nvec,
-                                                              const MapParams pre, const MapParams post) {
+                                                              const MapParams pre, const MapParams post, const bool wait_prev) {
     __shared__ uint4 stage[kThreads * 3];
     pdl_launch_dependents();
-    pdl_wait();
+    pdl_wait(wait_prev);
     const size_t base = (size_t)blockIdx.x * (kThreads * 3);
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
@@ -292,14 +292,15 @@ int launch_point_t(dip_ctx* ctx, const ImgView& src, const ImgView& dst, const M
         const size_t chunk = (size_t)kThreads * unroll;
         const size_t blocks = (nvec + chunk - 1) / chunk;
         if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-        DIP_CUDA(ctx, launch_kernel(point_flat_kernel<OP, unroll>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute,
-                                    reinterpret_cast<const uint4*>(src.base), reinterpret_cast<uint4*>(dst.base), nvec, m, post));
+        const LaunchMode mode = plan_launch(ctx, src, dst);
+        DIP_CUDA(ctx, launch_kernel(mode, point_flat_kernel<OP, unroll>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute,
+                                    reinterpret_cast<const uint4*>(src.base), reinterpret_cast<uint4*>(dst.base), nvec, m, post, mode != kNoWait));
     } else {
         const int vpr = (src.rowbytes + 15) / 16;
         const size_t total = (size_t)vpr * (size_t)src.height * (size_t)src.frames;
         const size_t blocks = (total + kThreads - 1) / kThreads;
         if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-        DIP_CUDA(ctx, launch_kernel(point_rows_kernel<OP>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, vpr, total, m, post));
+        DIP_CUDA(ctx, launch_kernel(plan_launch(ctx, nullptr, 0), point_rows_kernel<OP>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, vpr, total, m, post));
     }
     DIP_CHECK_LAUNCH(ctx, "point kernel");
     return DIP_OK;
@@ -324,8 +325,9 @@ int launch_gray3(dip_ctx* ctx, const ImgView& src, const ImgView& dst, const Map
         const size_t nvec = src.pitch * (size_t)src.height * (size_t)src.frames / 16;
         const size_t blocks = (nvec + kThreads * 3 - 1) / (kThreads * 3);
         if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-        DIP_CUDA(ctx, launch_kernel(gray3_flat_kernel<MAPPED>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute,
-                                    reinterpret_cast<const uint4*>(src.base), reinterpret_cast<uint4*>(dst.base), nvec, pre, post));
+        const LaunchMode mode = plan_launch(ctx, src, dst);
+        DIP_CUDA(ctx, launch_kernel(mode, gray3_flat_kernel<MAPPED>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute,
+                                    reinterpret_cast<const uint4*>(src.base), reinterpret_cast<uint4*>(dst.base), nvec, pre, post, mode != kNoWait));
         DIP_CHECK_LAUNCH(ctx, "gray3_flat_kernel");
         return DIP_OK;
     }
@@ -334,9 +336,9 @@ int launch_gray3(dip_ctx* ctx, const ImgView& src, const ImgView& dst, const Map
     const size_t blocks = (total + kThreads - 1) / kThreads;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
     if (exact_rows(src) || exact_rows(dst))
-        DIP_CUDA(ctx, launch_kernel(gray3_kernel<true, MAPPED>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total, pre, post));
+        DIP_CUDA(ctx, launch_kernel(plan_launch(ctx, nullptr, 0), gray3_kernel<true, MAPPED>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total, pre, post));
     else
-        DIP_CUDA(ctx, launch_kernel(gray3_kernel<false, MAPPED>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total, pre, post));
+        DIP_CUDA(ctx, launch_kernel(plan_launch(ctx, nullptr, 0), gray3_kernel<false, MAPPED>, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, groups, total, pre, post));
     DIP_CHECK_LAUNCH(ctx, "gray3_kernel");
     return DIP_OK;
 }
@@ -365,7 +367,7 @@ int launch_synth(dip_ctx* ctx, const ImgView& dst, uint32_t seed, uint64_t first
     const size_t total = (size_t)vpr * (size_t)dst.height * (size_t)dst.frames;
     const size_t blocks = (total + kThreads - 1) / kThreads;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-    DIP_CUDA(ctx, launch_kernel(synth_kernel, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, dst, seed, first_row, vpr, total));
+    DIP_CUDA(ctx, launch_kernel(plan_launch(ctx, nullptr, 0), synth_kernel, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, dst, seed, first_row, vpr, total));
     DIP_CHECK_LAUNCH(ctx, "synth_kernel");
     return DIP_OK;
 }
@@ -376,13 +378,14 @@ int launch_checksum(dip_ctx* ctx, const ImgView& src, uint64_t first_row, uint64
     if (src.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "more than 65535 frames");
     const unsigned bx = (unsigned)std::min<size_t>((vpf + kThreads - 1) / kThreads, (size_t)ctx->sm_count * 8);
     dim3 grid(bx ? bx : 1, (unsigned)src.frames);
-    DIP_CUDA(ctx, launch_kernel(checksum_kernel, grid, dim3(kThreads), 0, ctx->compute, src, vpr, vpf, first_row,
+    DIP_CUDA(ctx, launch_kernel(plan_launch(ctx, nullptr, 0), checksum_kernel, grid, dim3(kThreads), 0, ctx->compute, src, vpr, vpf, first_row,
                                 reinterpret_cast<unsigned long long*>(d_out)));
     DIP_CHECK_LAUNCH(ctx, "checksum_kernel");
     return DIP_OK;
 }
 
 int launch_fill(dip_ctx* ctx, uint8_t* p, size_t bytes, uint32_t value) {
+    dep_touch(ctx);
     DIP_CUDA(ctx, cudaMemsetAsync(p, (int)value, bytes, ctx->compute));
     return DIP_OK;
 }

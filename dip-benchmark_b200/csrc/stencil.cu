@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_co
         fence_barrier_init();
         mbar_expect_tx(bar, ROWS * kRowBytes);
     }
-    pdl_wait();
+    pdl_wait(p.wait_prev);
     if (threadIdx.x == 0) tma_load_3d(tile, &tmap, bar, (gx0 - kHalo) / 4, ytop, f);
     __syncthreads();
     mbar_wait(bar, 0);
@@ -226,7 +226,9 @@ int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const 
         DIP_CUDA(ctx, cudaFuncSetAttribute(fused_g5e3_kernel<C, R, kWarps, MAPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
-    DIP_CUDA(ctx, launch_kernel(fused_g5e3_kernel<C, R, kWarps, MAPPED>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
+    const LaunchMode mode = plan_tiled_launch(ctx, src, dst, g);
+    p.wait_prev = mode != kNoWait;
+    DIP_CUDA(ctx, launch_kernel(mode, fused_g5e3_kernel<C, R, kWarps, MAPPED>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
                                 dim3(kWarps * 32), smem_bytes, ctx->compute, *map, p));
     DIP_CHECK_LAUNCH(ctx, "fused_g5e3_kernel");
     return DIP_OK;
@@ -347,7 +349,7 @@ int launch_generic(dip_ctx* ctx, const GenericParams& p) {
     if (total == 0) return DIP_OK;
     const size_t blocks = (total + 255) / 256;
     if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-    DIP_CUDA(ctx, launch_kernel(generic_kernel<MODE>, dim3((unsigned)blocks), dim3(256), 0, ctx->compute, p));
+    DIP_CUDA(ctx, launch_kernel(plan_launch(ctx, nullptr, 0), generic_kernel<MODE>, dim3((unsigned)blocks), dim3(256), 0, ctx->compute, p));
     DIP_CHECK_LAUNCH(ctx, "generic_kernel");
     return DIP_OK;
 }

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kGenWarps * 32) generic_tiled_kernel(const __g
         fence_barrier_init();
         mbar_expect_tx(bar, rows * kRowBytes);
     }
-    pdl_wait();
+    pdl_wait(p.wait_prev);
     if (threadIdx.x == 0) tma_load_3d(tile, &tmap, bar, (bx0 - kHalo) / 4, ytop, f);
     __syncthreads();
     mbar_wait(bar, 0);
@@ -182,7 +182,9 @@ int launch_generic_tiled_t(dip_ctx* ctx, const dip_image* src, dip_image* dst, c
     p.dst_exact = exact_rows(dst->v);
     if (p.tiles_x <= 0 || p.tiles_y <= 0) return DIP_OK;
     if (p.tiles_y > 65535 || src->v.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-    DIP_CUDA(ctx, launch_kernel(generic_tiled_kernel<MODE, C, RX>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
+    const LaunchMode mode = plan_tiled_launch(ctx, src, dst, g);
+    p.wait_prev = mode != kNoWait;
+    DIP_CUDA(ctx, launch_kernel(mode, generic_tiled_kernel<MODE, C, RX>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
                                 dim3(kGenWarps * 32), smem_bytes, ctx->compute, *map, p, taps));
     DIP_CHECK_LAUNCH(ctx, "generic_tiled_kernel");
     return DIP_OK;

@@ -54,7 +54,7 @@ __host__ __device__ constexpr bool op_is_morph(int op) { return op <= kDilateCro
 
 // Resident CTAs per SM the register allocation must allow (0 = whatever ptxas picks).  The packed-half 1x5+5x1 kernel
 // comes out at 89 registers (5 CTAs of 4 warps) without the bound; it is issue-bound and wants the 6 the tile allows.
-__host__ __device__ constexpr int op_min_ctas(int op) { return op == kConv5Sep ? 6 : 1; }
+__host__ __device__ constexpr int op_min_ctas(int op) { return op == kConv5Sep ? 6 : 0; }  // 0 = no bound (a bound of 1 makes ptxas spend registers freely)
 #ifndef DIP_EVEN_PRMT5
 #define DIP_EVEN_PRMT5 6
 #endif
@@ -69,6 +69,7 @@ struct StencilParams {
     int dst_y0;              // dst row receiving out_y0
     int tiles_x, tiles_y;
     bool dst_exact;          // dst rows are not padded to 16 bytes (wrapped region of interest)
+    bool wait_prev;          // execute griddepcontrol.wait (false: proven independent of every unfinished kernel, plan_launch)
     // Mosaic bands (dip_apply_rows_peer): source rows [peer_top_y0, peer_top_y1) / [peer_bot_y0, peer_bot_y1) are not in
     // this GPU's band buffer but in the neighbour's, which is mapped into this process (CUDA IPC, NVLink): the CTAs whose
     // tile covers such rows read them straight from the peer.  peer_* point at the peer byte that corresponds to byte 0
@@ -696,7 +697,7 @@ __global__ void __launch_bounds__(kWarps * 32, op_min_ctas(OP)) stencil_kernel(c
         fence_barrier_init();
         mbar_expect_tx(bar, ROWS * kRowBytes);
     }
-    pdl_wait();  // the previous kernel's writes are visible from here on
+    pdl_wait(p.wait_prev);  // the previous kernels' writes are visible from here on
     if (threadIdx.x == 0) tma_load_3d(tile, &tmap, bar, (bx0 - kHalo) / 4, ytop, f);
     __syncthreads();  // barrier init visible to the waiters
     mbar_wait(bar, 0);
@@ -705,6 +706,13 @@ __global__ void __launch_bounds__(kWarps * 32, op_min_ctas(OP)) stencil_kernel(c
 }
 
 bool g_no_occupancy_pad = false;  // development knob "no_pad"
+
+// a tiled launch reads the source view and writes the destination view; rows that come from a neighbour GPU are memory
+// this process knows nothing about (ordered by the caller's flags / barriers), so such a launch is never a no-wait one
+inline LaunchMode plan_tiled_launch(dip_ctx* ctx, const dip_image* src, const dip_image* dst, const RowGeom& g) {
+    if (g.peer_top || g.peer_bot) return plan_launch(ctx, nullptr, 0);
+    return plan_launch(ctx, src->v, dst->v);
+}
 
 // fills the source-side fields every tiled launch shares
 inline void fill_peer_params(StencilParams& p, const dip_image* src, const RowGeom& g) {
@@ -755,7 +763,9 @@ int launch_tiled(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGe
         DIP_CUDA(ctx, cudaFuncSetAttribute(stencil_kernel<OP, C, R, kWarps, MAPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, std::max(kPadded, kTileSmem)));
         attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
-    DIP_CUDA(ctx, launch_kernel(stencil_kernel<OP, C, R, kWarps, MAPPED>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames), dim3(kThreads), smem_bytes, ctx->compute, *map, p));
+    const LaunchMode mode = plan_tiled_launch(ctx, src, dst, g);
+    p.wait_prev = mode != kNoWait;
+    DIP_CUDA(ctx, launch_kernel(mode, stencil_kernel<OP, C, R, kWarps, MAPPED>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames), dim3(kThreads), smem_bytes, ctx->compute, *map, p));
     DIP_CHECK_LAUNCH(ctx, "stencil_kernel");
     return DIP_OK;
 }

@@ -94,3 +94,56 @@ OPERATIONS = [
     ("convolution-gaussian-blur-5x5-separated", _keep_shape(lambda im: filter2d_separable(im, _o.BLUR_5X5_1X5, _o.BLUR_5X5_5X1))),
     ("gaussian-blur-3x3", _keep_shape(gaussian_blur3x3)),
 ]
+
+
+class ReferenceLoop:
+    """The reference's ``perform_benchmark`` state and closures, as written (opencv:41-105): three ``cv.UMat`` images
+    ``image`` / ``aux`` / ``sample`` allocated once, every operation called with its destination argument so that it
+    writes into the pre-allocated ``sample`` (the separable ones through ``aux``), ``cv.copyTo(image, sample)`` with
+    ``sample`` in the mask slot exactly like opencv:94.  bench.py's ``--impl reference`` arm and its ``cpu_baseline``
+    time THIS; the functional wrappers above exist for the golden vectors.  One instance per worker thread."""
+
+    def __init__(self, cpu_image: np.ndarray):
+        self.image = cv.UMat(cpu_image)      # opencv:42-44
+        self.aux = cv.UMat(cpu_image)
+        self.sample = cv.UMat(cpu_image)
+        image, aux, sample = self.image, self.aux, self.sample
+        o = _o
+
+        def erosion_separated():             # opencv:76-78
+            cv.erode(image, o.SQUARE_MASK_1X3, aux)
+            cv.erode(aux, o.SQUARE_MASK_3X1, sample)
+
+        def convolution_3x3_separated():     # opencv:84-86
+            cv.filter2D(image, -1, o.BLUR_3X3_1X3, aux)
+            cv.filter2D(aux, -1, o.BLUR_3X3_3X1, sample)
+
+        def convolution_5x5_separated():     # opencv:88-90
+            cv.filter2D(image, -1, o.BLUR_5X5_1X5, aux)
+            cv.filter2D(aux, -1, o.BLUR_5X5_5X1, sample)
+
+        self.operations = [                  # opencv:94-105, same order, same calls
+            ("copy", lambda: cv.copyTo(image, sample)),
+            ("inversion", lambda: cv.bitwise_not(image, sample)),
+            ("grayscale", lambda: cv.cvtColor(cv.cvtColor(image, cv.COLOR_BGR2GRAY), cv.COLOR_GRAY2BGR, sample)),
+            ("threshold", lambda: cv.threshold(image, 127, 255, cv.THRESH_BINARY, sample)),
+            ("erosion-cross", lambda: cv.erode(image, o.CROSS_MASK, sample)),
+            ("erosion-square", lambda: cv.erode(image, o.SQUARE_MASK, sample)),
+            ("erosion-square-separated", erosion_separated),
+            ("convolution-gaussian-blur-3x3", lambda: cv.filter2D(image, -1, o.BLUR_3X3, sample)),
+            ("convolution-gaussian-blur-3x3-separated", convolution_3x3_separated),
+            ("convolution-gaussian-blur-5x5", lambda: cv.filter2D(image, -1, o.BLUR_5X5, sample)),
+            ("convolution-gaussian-blur-5x5-separated", convolution_5x5_separated),
+            ("gaussian-blur-3x3", lambda: cv.GaussianBlur(image, (3, 3), 0, sample)),
+        ]
+
+    def load(self, cpu_image: np.ndarray) -> None:
+        """A new input frame into the pre-allocated ``image`` (the reference uploads once, opencv:42)."""
+        cv.copyTo(cpu_image, None, self.image)
+
+    def run_all(self) -> None:
+        for _, fn in self.operations:
+            fn()
+
+    def result(self) -> np.ndarray:          # opencv:113 ``sample.get()``
+        return self.sample.get()

@@ -78,12 +78,26 @@ def test_bench_reference_arm_prints_one_json_line():
     import json
     import sys
     out = subprocess.check_output([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
-                                   "--cpu-frames", "1"], text=True)
+                                   "--batch", "8"], text=True)
     lines = [l for l in out.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "Mpixel/s" and d["cpu_baseline"]["kind"] in ("reference", "port")
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["value"] > 0
+    # both variants of BASELINE.md 3: all host cores (the line's value) and the reference-faithful single stream of calls
+    assert d["cpu_baseline"]["all_cores"]["value"] == d["value"] and d["cpu_baseline"]["faithful"]["value"] > 0
+    assert d["config"]["frames_total"] == 8 and d["detail"]["cv2_num_threads"] is not None
+
+
+def test_both_bench_arms_describe_the_same_config():
+    """The driver compares the two arms' `config`: they must be equal for equal arguments."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.config_dict(256) == bench.config_dict(256) and "frames_total" in bench.config_dict(256)
+    src = open(os.path.join(ROOT, "bench.py")).read()
+    assert src.count('"config": config_dict(args.batch)') == 2   # one per arm, nothing arm-specific inside
 
 
 def test_chain_planner_counts_passes_without_a_gpu():

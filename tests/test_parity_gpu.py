@@ -313,6 +313,23 @@ def test_mosaic_iterated_steps_under_the_flag_protocol(ctx, dip, orc, halo):
                 assert ctx.flag_read(bands[0].flags, 1) == steps and ctx.flag_read(bands[-1].flags, 0) == steps
             for b in bands:
                 b.close()
+    # the oracle's checksum of the pipeline applied twice (tests/golden/make_mosaic_kat.py <side> 1024 2)
+    import json
+    with open(os.path.join(ROOT, "tests", "golden", "mosaic_kat.json")) as f:
+        kat = json.load(f)
+    for world in (1, 4):
+        bands = [dip.mosaic.MosaicBand(ctx, 4096, 4096, world, r, fused=True, halo=halo, iterate=True) for r in range(world)]
+        for b in bands:
+            b.fill_synthetic(seed=0)
+        for b in bands:
+            b.connect_local(bands)
+        for s in range(2):
+            for b in bands:
+                b.step()
+        got = sum(b.checksum() for b in bands) & 0xFFFFFFFFFFFFFFFF
+        for b in bands:
+            b.close()
+        assert f"{got:016x}" == kat["4096_iter2"], world
 
 
 @pytest.mark.parametrize("halo", ["kernel", "copy"])
@@ -384,7 +401,7 @@ def test_mosaic_known_answer_checksums(ctx, dip):
     import json
     with open(os.path.join(ROOT, "tests", "golden", "mosaic_kat.json")) as f:
         kat = json.load(f)
-    for side_s, want in sorted(kat.items(), key=lambda kv: int(kv[0])):
+    for side_s, want in sorted(((k, v) for k, v in kat.items() if k.isdigit()), key=lambda kv: int(kv[0])):
         side = int(side_s)
         for world in (1, 8):
             if side >= 65536 and world == 8:
@@ -559,7 +576,7 @@ def test_mosaic_fused_chain_known_answers(ctx, dip):
     import json
     with open(os.path.join(ROOT, "tests", "golden", "mosaic_kat.json")) as f:
         kat = json.load(f)
-    for side_s, want in sorted(kat.items(), key=lambda kv: int(kv[0])):
+    for side_s, want in sorted(((k, v) for k, v in kat.items() if k.isdigit()), key=lambda kv: int(kv[0])):
         side = int(side_s)
         for world in ((1, 3, 8) if side < 65536 else (1,)):
             bands = [dip.mosaic.MosaicBand(ctx, side, side, world, r, fused=True) for r in range(world)]
@@ -978,3 +995,50 @@ def test_graph_replay_of_the_operation_list(ctx, dip, orc):
     src.close(); chain_out.close()
     for o in outs:
         o.close()
+
+
+def test_independent_calls_overlap_and_dependent_ones_wait(ctx, dip, orc):
+    """The library skips the inter-kernel dependency wait between operations it has proven independent (plan_launch).
+    Random programs over a pool of images -- reads after writes, writes after reads, writes after writes, in-place point
+    ops, transfers and checksums in between -- must give exactly what the same program gives on the CPU."""
+    rng = np.random.default_rng(2026)
+    h, w, c = 900, 1700, 3          # large enough that consecutive kernels really overlap
+    ops = {
+        "invert": (lambda s, d: ctx.invert(s, d), lambda a: 255 - a, True),
+        "threshold": (lambda s, d: ctx.threshold(s, d, 100, 200), lambda a: orc.threshold(a, 100, 200), True),
+        "gray": (lambda s, d: ctx.grayscale(s, d), orc.grayscale, True),
+        "erode": (lambda s, d: ctx.erode(s, d, dip.ops.SQUARE_MASK), lambda a: orc.erode(a, orc.SQUARE_MASK), False),
+        "conv5sep": (lambda s, d: ctx.convolve_separable(s, d, orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1),
+                     lambda a: orc.filter2d_separable(a, orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1), False),
+        "blur": (lambda s, d: ctx.gaussian_blur3x3(s, d), orc.gaussian_blur3x3, False),
+    }
+    names = list(ops)
+    for trial in range(3):
+        n = 6
+        host = [rng.integers(0, 256, (h, w, c), dtype=np.uint8) for _ in range(n)]
+        dev = [ctx.from_array(a) for a in host]
+        ctx.sync()
+        for step in range(70):
+            name = names[int(rng.integers(len(names)))]
+            gpu_fn, cpu_fn, inplace_ok = ops[name]
+            s = int(rng.integers(n))
+            d = int(rng.integers(n))
+            if d == s and not inplace_ok:
+                d = (s + 1) % n
+            gpu_fn(dev[s], dev[d])
+            host[d] = cpu_fn(host[s])
+            r = rng.random()
+            if r < 0.08:      # a transfer in the middle of the program
+                k = int(rng.integers(n))
+                assert np.array_equal(dev[k].download(), host[k]), (trial, step, "download")
+            elif r < 0.14:
+                k = int(rng.integers(n))
+                host[k] = rng.integers(0, 256, (h, w, c), dtype=np.uint8)
+                dev[k].upload(host[k])
+            elif r < 0.18:
+                k = int(rng.integers(n))
+                assert dev[k].checksum()[0] == orc.checksum(host[k]), (trial, step, "checksum")
+        for k in range(n):
+            assert np.array_equal(dev[k].download(), host[k]), (trial, k)
+        for im in dev:
+            im.close()
