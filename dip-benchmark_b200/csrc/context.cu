@@ -138,12 +138,12 @@ static PFN_encodeTiled encode_tiled_fn() {
     return fn;
 }
 
-int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out) {
+int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out, bool swizzle128) {
     const ImgView& v = img->v;
     dip_image* root = root_of(img);
     for (const TmapKey& k : root->tmaps)
         if (k.base == v.base && k.pitch == v.pitch && k.frame_stride == v.frame_stride && k.rowbytes == v.rowbytes &&
-            k.height == v.height && k.frames == v.frames && k.box_words == box_words && k.box_rows == box_rows) {
+            k.height == v.height && k.frames == v.frames && k.box_words == box_words && k.box_rows == box_rows && k.swizzle128 == swizzle128) {
             *out = &k.map;
             return DIP_OK;
         }
@@ -156,6 +156,7 @@ int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CU
     key.rowbytes = v.rowbytes; key.height = v.height; key.frames = v.frames;
     key.box_words = box_words;
     key.box_rows = box_rows;
+    key.swizzle128 = swizzle128;
     // (x in 4-byte words, y, frame): u32 elements lift the 256-element box limit to 1 KiB rows.  The x extent is
     // the row's own (16-byte padded) length, not the pitch: a wrapped region of interest must never be read past
     // its right edge (TMA zero-fills there and the border patch supplies the halo).
@@ -166,7 +167,7 @@ int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CU
     cuuint32_t box[3] = {(cuuint32_t)box_words, (cuuint32_t)box_rows, 1};
     cuuint32_t estr[3] = {1, 1, 1};
     CUresult r = enc(&key.map, CU_TENSOR_MAP_DATA_TYPE_UINT32, 3, v.base, dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                      CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS)
         return fail(ctx, DIP_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d) for %dx%d pitch %zu box %dx%d",

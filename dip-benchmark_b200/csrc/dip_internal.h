@@ -37,6 +37,7 @@ struct TmapKey {
     size_t pitch, frame_stride;
     int rowbytes, height, frames;
     int box_words, box_rows;
+    bool swizzle128;      // CU_TENSOR_MAP_SWIZZLE_128B (the tensor-core kernel's operand layout); box_words must be 32
     CUtensorMap map;
 };
 
@@ -325,7 +326,11 @@ struct SmallTaps {
 int launch_generic_tiled(dip_ctx* ctx, int mode, int kw, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps);
 
 // TMA descriptor of an image view seen as a (pitch/4 words, rows, frames) u32 tensor.
-int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out);
+int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out, bool swizzle128 = false);
+
+// gauss_umma.cu: the fused 1x5+5x1 Gaussian on the tensor cores (tcgen05.mma.kind::i8)
+bool umma_gauss5sep_ok(const dip_image* src, const dip_image* dst, const RowGeom& g);
+int launch_gauss5sep_umma(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g);
 
 inline dip_image* root_of(dip_image* im) {
     while (im && im->parent) im = im->parent;

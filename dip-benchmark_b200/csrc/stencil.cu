@@ -41,7 +41,9 @@ namespace {
 // Development knobs (dip_debug_set): "tile_rows" 0 = automatic, 64 or 32 forces the tile height.
 // "int_math" 1 = the packed-integer forms of the two separable Gaussians instead of the packed-half ones (A/B only).
 // "direct_generic" 1 = arbitrary small masks / kernels through the direct kernel instead of the tiled generic one (A/B only).
-struct Knobs { int tile_rows = 0; int int_math = 0; int direct_generic = 0; };
+// "umma" 1 = the fused 1x5+5x1 Gaussian on the tensor cores (gauss_umma.cu: tcgen05.mma.kind::i8, bit-exact, but 15.9 us
+// per frame against 10.4 for the packed-half SIMD kernel so far -- profiles/r2_umma_experiment.md) instead of the SIMD kernel.
+struct Knobs { int tile_rows = 0; int int_math = 0; int direct_generic = 0; int umma = 0; };
 Knobs g_knobs;
 
 // One warp band of the fused Gaussian -> erosion kernel below.  EDGE: the tile touches the image rim, so Gaussian
@@ -281,6 +283,7 @@ int launch_tiled_op(dip_ctx* ctx, int op, const dip_image* src, dip_image* dst, 
         maps = &moved;
     }
     if (maps && !(maps->pre.identity() && maps->post.identity())) return launch_tiled_mapped(ctx, op, src, dst, g, *maps);
+    if (op == kConv5Sep && g_knobs.umma && !g_knobs.int_math && umma_gauss5sep_ok(src, dst, g)) return launch_gauss5sep_umma(ctx, src, dst, g);
     if (g_knobs.int_math) op = op == kConv3Sep ? kConv3SepI : op == kConv5Sep ? kConv5SepI : op;
     switch (op) {
 #define DIP_T(OP) case OP: return launch_tiled_c<OP>(ctx, src, dst, g);
@@ -570,6 +573,7 @@ int dip_debug_set(const char* key, int value) {
     if (!strcmp(key, "tile_rows")) g_knobs.tile_rows = value;
     else if (!strcmp(key, "int_math")) g_knobs.int_math = value;
     else if (!strcmp(key, "direct_generic")) g_knobs.direct_generic = value;
+    else if (!strcmp(key, "umma")) g_knobs.umma = value;
     else if (!strcmp(key, "no_pad")) g_no_occupancy_pad = value != 0;
     else return fail(nullptr, DIP_ERR_ARG, "unknown knob %s", key);
     return DIP_OK;

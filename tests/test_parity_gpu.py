@@ -1042,3 +1042,37 @@ def test_independent_calls_overlap_and_dependent_ones_wait(ctx, dip, orc):
             assert np.array_equal(dev[k].download(), host[k]), (trial, k)
         for im in dev:
             im.close()
+
+
+def test_tensor_core_gaussian_is_bit_exact(ctx, dip, orc, kat):
+    """gauss_umma.cu (knob "umma"): the fused 1x5+5x1 Gaussian as two banded-Toeplitz tcgen05.mma.kind::i8 products with
+    TMEM accumulators.  Same bits as the SIMD kernel and the oracle: edge shapes, 1/3/4 channels, stacks, row bands, and
+    the full-size known answer."""
+    L = dip.lib()
+    L.dip_debug_set(b"umma", 1)
+    try:
+        rng = np.random.default_rng(55)
+        for c in (1, 3, 4):
+            for (h, w) in [(8, 8), (9, 40), (123, 31), (124, 32), (125, 33), (130, 200), (260, 97), (400, 1100)]:
+                img = rand_img(rng, h, w, c)
+                got = run_op(ctx, "convolve_separable", (orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1), img)
+                assert np.array_equal(got, orc.filter2d_separable(img, orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1)), (c, h, w)
+        stack = rng.integers(0, 256, (5, 300, 517, 3), dtype=np.uint8)
+        got = run_op(ctx, "convolve_separable", (orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1), stack)
+        for f in range(5):
+            assert np.array_equal(got[f], orc.filter2d_separable(stack[f], orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1)), f
+        # row bands (dip_apply_rows): interior band edges read real rows, true edges reflect
+        img = rand_img(rng, 700, 333, 1)
+        want = orc.filter2d_separable(img, orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1)
+        src = ctx.from_array(img)
+        dst = ctx.image_like(src)
+        op = {p: o for _, p, o in ctx.reference_ops()}["convolution-gaussian-blur-5x5-separated"]
+        for (r0, r1) in ((0, 250), (250, 520), (520, 700)):
+            ctx.apply_rows(op, src, 0, 700, r0, r1 - r0, dst, r0)
+        assert np.array_equal(dst.download().reshape(img.shape), want)
+        src.close(); dst.close()
+        B = np.random.default_rng(0).integers(0, 256, (2336, 3504, 3), dtype=np.uint8)
+        got = run_op(ctx, "convolve_separable", (orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1), B)
+        assert digest(got) == kat["outputs"]["B_rng0"]["convolution-gaussian-blur-5x5-separated"]
+    finally:
+        L.dip_debug_set(b"umma", 0)
