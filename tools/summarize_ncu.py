@@ -30,7 +30,7 @@ for row in csv.DictReader(lines):
     v = float(row["Metric Value"].replace(",", "")) / 1e3
     agg.setdefault((short(row["Kernel Name"]), row["Grid Size"], row["Block Size"]), []).append(v)
 tot = sum(sum(v) for v in agg.values())
-out = [f"# {tag} ncu launch list: `python bench.py --steps 2 --warmup 3 --no-e2e --no-cpu` (B200, --clock-control none)", "",
+out = [f"# {tag} ncu launch list: `python bench.py --no-e2e --no-cpu --no-mosaic --no-single --steps 1 --warmup 3 --min-timed-s 0 --batch {FRAMES}` (B200, --clock-control none)", "",
        "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv`: cold-cache, serialised launches; compare SHARES.", "",
        "| kernel | grid | block | launches | mean us | share |", "|---|---|---|---|---|---|"]
 for (k, g, b), v in agg.items():
