@@ -149,6 +149,11 @@ def lib() -> C.CDLL:
         "dip_flag_signal": ([vp, vp, i, C.c_uint32], i),
         "dip_flag_wait": ([vp, vp, i, C.c_uint32], i),
         "dip_flag_read": ([vp, vp, i, P(C.c_uint32)], i),
+        "dip_jpeg_info": ([vp, vp, sz, P(i), P(i), P(i)], i),
+        "dip_jpeg_decode": ([vp, vp, sz, vp, i], i),
+        "dip_jpeg_decode_batch": ([vp, P(vp), P(sz), i, vp, i], i),
+        "dip_jpeg_encode": ([vp, vp, i, i, vp, sz, P(sz)], i),
+        "dip_jpeg_backend": ([vp], C.c_char_p),
         "dip_debug_set": ([C.c_char_p, i], i),
     }
     for name, (args, res) in sig.items():

@@ -270,6 +270,7 @@ int dip_shutdown(dip_ctx* ctx) {
     cudaStreamSynchronize(ctx->download);
     cudaStreamSynchronize(ctx->halo);
     for (dip_image*& sc : ctx->scratch) { dip_image_destroy(sc); sc = nullptr; }
+    jpeg_release(ctx);
     for (int i = 0; i < dip_ctx::kSlots; ++i) {
         if (ctx->stage_up[i]) cudaFreeHost(ctx->stage_up[i]);
         if (ctx->stage_dn[i]) cudaFreeHost(ctx->stage_dn[i]);

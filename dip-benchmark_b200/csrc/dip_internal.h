@@ -122,6 +122,7 @@ struct dip_ctx {
     dip::DepTracker dep;
     bool capturing = false;              // between dip_graph_begin and dip_graph_end: kernels are recorded, not run
     uint64_t capture_launches0 = 0;
+    void* jpeg = nullptr;                // jpeg.cu's codec state (nvJPEG handles), created on first use
     std::string last_error;
 };
 
@@ -327,6 +328,9 @@ int launch_generic_tiled(dip_ctx* ctx, int mode, int kw, const dip_image* src, d
 
 // TMA descriptor of an image view seen as a (pitch/4 words, rows, frames) u32 tensor.
 int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out, bool swizzle128 = false);
+
+// jpeg.cu: releases the ctx's codec state (dip_shutdown)
+void jpeg_release(dip_ctx* ctx);
 
 // gauss_umma.cu: the fused 1x5+5x1 Gaussian on the tensor cores (tcgen05.mma.kind::i8)
 bool umma_gauss5sep_ok(const dip_image* src, const dip_image* dst, const RowGeom& g);

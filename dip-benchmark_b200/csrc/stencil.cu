@@ -43,7 +43,8 @@ namespace {
 // "direct_generic" 1 = arbitrary small masks / kernels through the direct kernel instead of the tiled generic one (A/B only).
 // "umma" 1 = the fused 1x5+5x1 Gaussian on the tensor cores (gauss_umma.cu: tcgen05.mma.kind::i8, bit-exact, but 15.9 us
 // per frame against 10.4 for the packed-half SIMD kernel so far -- profiles/r2_umma_experiment.md) instead of the SIMD kernel.
-struct Knobs { int tile_rows = 0; int int_math = 0; int direct_generic = 0; int umma = 0; };
+// "fused_shape": band rows x warps (and a register cap) of the fused Gaussian -> erosion kernel on one-channel images (A/B only).
+struct Knobs { int tile_rows = 0; int int_math = 0; int direct_generic = 0; int umma = 0; int fused_shape = 0; };
 Knobs g_knobs;
 
 // One warp band of the fused Gaussian -> erosion kernel below.  EDGE: the tile touches the image rim, so Gaussian
@@ -138,8 +139,8 @@ __device__ __forceinline__ void fused_band(const uint8_t* colp, const StencilPar
 // one lane; a warp computes R+2 Gaussian rows for R output rows.  No second shared-memory tile, no
 // __syncthreads after the load.
 // =================================================================================================
-template <int C, int R, int kWarps, bool MAPPED>
-__global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
+template <int C, int R, int kWarps, bool MAPPED, int kMinCtas = 0>
+__global__ void __launch_bounds__(kWarps * 32, kMinCtas) fused_g5e3_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
     constexpr int kThreads = kWarps * 32;
     constexpr int TO = kWarps * R;        // output rows per tile
     constexpr int ROWS = TO + 6;          // source rows per tile (Gaussian rows TO + 2, each needing +-2)
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(kWarps * 32) fused_g5e3_kernel(const __grid_co
     }
 }
 
-template <int C, int R, int kWarps, bool MAPPED>
+template <int C, int R, int kWarps, bool MAPPED, int kMinCtas = 0>
 int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps) {
     constexpr int TO = kWarps * R, ROWS = TO + 6;
     constexpr int smem_bytes = ROWS * kRowBytes + 16;
@@ -225,12 +226,12 @@ int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const 
     static std::atomic<uint64_t> attr_set{0};
     const uint64_t dev_bit = 1ull << (ctx->device & 63);
     if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
-        DIP_CUDA(ctx, cudaFuncSetAttribute(fused_g5e3_kernel<C, R, kWarps, MAPPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        DIP_CUDA(ctx, cudaFuncSetAttribute(fused_g5e3_kernel<C, R, kWarps, MAPPED, kMinCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
     const LaunchMode mode = plan_tiled_launch(ctx, src, dst, g);
     p.wait_prev = mode != kNoWait;
-    DIP_CUDA(ctx, launch_kernel(mode, fused_g5e3_kernel<C, R, kWarps, MAPPED>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
+    DIP_CUDA(ctx, launch_kernel(mode, fused_g5e3_kernel<C, R, kWarps, MAPPED, kMinCtas>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
                                 dim3(kWarps * 32), smem_bytes, ctx->compute, *map, p));
     DIP_CHECK_LAUNCH(ctx, "fused_g5e3_kernel");
     return DIP_OK;
@@ -549,7 +550,18 @@ int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, co
     if (rc != DIP_OK) return rc;
     const bool mapped = maps && !(maps->pre.identity() && maps->post.identity());
     switch (src->v.channels) {
-        case 1: return mapped ? launch_fused_g5e3<1, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<1, 15, 4, false>(ctx, src, dst, g, nullptr);
+        case 1:
+            if (!mapped) switch (g_knobs.fused_shape) {
+                case 1: return launch_fused_g5e3<1, 30, 2, false>(ctx, src, dst, g, nullptr);
+                case 2: return launch_fused_g5e3<1, 30, 4, false>(ctx, src, dst, g, nullptr);
+                case 3: return launch_fused_g5e3<1, 15, 4, false, 5>(ctx, src, dst, g, nullptr);
+                case 4: return launch_fused_g5e3<1, 15, 2, false>(ctx, src, dst, g, nullptr);
+                case 5: return launch_fused_g5e3<1, 30, 3, false>(ctx, src, dst, g, nullptr);
+                case 6: return launch_fused_g5e3<1, 15, 4, false, 6>(ctx, src, dst, g, nullptr);
+                case 7: return launch_fused_g5e3<1, 45, 2, false>(ctx, src, dst, g, nullptr);
+                default: break;
+            }
+            return mapped ? launch_fused_g5e3<1, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<1, 15, 4, false>(ctx, src, dst, g, nullptr);
         case 3: return mapped ? launch_fused_g5e3<3, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<3, 15, 4, false>(ctx, src, dst, g, nullptr);
         case 4: return mapped ? launch_fused_g5e3<4, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<4, 15, 4, false>(ctx, src, dst, g, nullptr);
     }
@@ -574,6 +586,7 @@ int dip_debug_set(const char* key, int value) {
     else if (!strcmp(key, "int_math")) g_knobs.int_math = value;
     else if (!strcmp(key, "direct_generic")) g_knobs.direct_generic = value;
     else if (!strcmp(key, "umma")) g_knobs.umma = value;
+    else if (!strcmp(key, "fused_shape")) g_knobs.fused_shape = value;
     else if (!strcmp(key, "no_pad")) g_no_occupancy_pad = value != 0;
     else return fail(nullptr, DIP_ERR_ARG, "unknown knob %s", key);
     return DIP_OK;

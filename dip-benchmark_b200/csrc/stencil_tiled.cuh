@@ -56,9 +56,13 @@ __host__ __device__ constexpr bool op_is_morph(int op) { return op <= kDilateCro
 // comes out at 89 registers (5 CTAs of 4 warps) without the bound; it is issue-bound and wants the 6 the tile allows.
 __host__ __device__ constexpr int op_min_ctas(int op) { return op == kConv5Sep ? 6 : 0; }  // 0 = no bound (a bound of 1 makes ptxas spend registers freely)
 #ifndef DIP_EVEN_PRMT5
-#define DIP_EVEN_PRMT5 6
+#define DIP_EVEN_PRMT5 8
 #endif
 constexpr int kEvenPrmt5 = DIP_EVEN_PRMT5;  // packed-half 1x5+5x1: words per row whose even bytes come from a PRMT
+#ifndef DIP_CASCADE_HALF
+#define DIP_CASCADE_HALF 6
+#endif
+constexpr int kCascadeHalf = DIP_CASCADE_HALF;  // packed-half 1x5+5x1: packed lanes (of 8) whose vertical pass is the all-half cascade
 
 struct StencilParams {
     ImgView dst;
@@ -259,18 +263,20 @@ constexpr uint32_t kH16th = 0x2C002C00u;     // half2(1/16)
 constexpr uint32_t kHNeg2048u = 0x88008800u; // half2(-2048 * 2^-24) = -2^-13
 constexpr uint32_t kH128u = 0x00800080u;     // half2(128 * 2^-24): the bit pattern of the byte 128
 // RNE((a + 4 b + 6 c + 4 d + e) / 16) per lane; ae = a + e and bd = b + d are plain integer sums (<= 510)
-__device__ __forceinline__ uint32_t half_gauss5(uint32_t ae, uint32_t bd, uint32_t c) {
+// `addend` = 128 u gives the u8 result as the lane's bit pattern; 0 gives the half (result - 128) u (see "vertical cascade")
+__device__ __forceinline__ uint32_t half_gauss5(uint32_t ae, uint32_t bd, uint32_t c, uint32_t addend = kH128u) {
     const uint32_t s = hadd2(hfma2(bd, kH4, hfma2(c, kH6, kHNeg2048u)), ae);  // S - 2048, exact
-    return hfma2(s, kH16th, kH128u);
+    return hfma2(s, kH16th, addend);
 }
 // RNE((a + 2 b + c) / 4) per lane; ac = a + c (<= 510)
 __device__ __forceinline__ uint32_t half_gauss3(uint32_t ac, uint32_t b) { return hmul2(hfma2(b, kH2, ac), kHQuarter); }
 
-template <int C>
+// CENTRED: the first CENTRED packed results come out as halves (result - 128) u instead of byte patterns
+template <int C, int CENTRED = 0>
 __device__ __forceinline__ void hgauss5_half(const Row8& r, Acc8& h) {
 #define DIP_H5H(j)                                                                                                   \
-    h.v[2 * j] = half_gauss5(pair_at<4 * j - 2 * C>(r) + pair_at<4 * j + 2 * C>(r), pair_at<4 * j - C>(r) + pair_at<4 * j + C>(r), r.e[2 + j]); \
-    h.v[2 * j + 1] = half_gauss5(pair_at<4 * j + 1 - 2 * C>(r) + pair_at<4 * j + 1 + 2 * C>(r), pair_at<4 * j + 1 - C>(r) + pair_at<4 * j + 1 + C>(r), r.o[2 + j]);
+    h.v[2 * j] = half_gauss5(pair_at<4 * j - 2 * C>(r) + pair_at<4 * j + 2 * C>(r), pair_at<4 * j - C>(r) + pair_at<4 * j + C>(r), r.e[2 + j], 2 * j < CENTRED ? 0u : kH128u); \
+    h.v[2 * j + 1] = half_gauss5(pair_at<4 * j + 1 - 2 * C>(r) + pair_at<4 * j + 1 + 2 * C>(r), pair_at<4 * j + 1 - C>(r) + pair_at<4 * j + 1 + C>(r), r.o[2 + j], 2 * j + 1 < CENTRED ? 0u : kH128u);
     DIP_H5H(0) DIP_H5H(1) DIP_H5H(2) DIP_H5H(3)
 #undef DIP_H5H
 }
@@ -540,26 +546,59 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
             h0 = h1; h1 = h2;
         }
     } else if constexpr (OP == kConv5Sep) {
-        // RNE([1 4 6 4 1]/16) rows -> u8 -> RNE([1 4 6 4 1]/16) columns in packed half precision
-        Acc8 h0, h1, h2, h3, h4;
+        // RNE([1 4 6 4 1]/16) rows -> u8 -> RNE([1 4 6 4 1]/16) columns in packed half precision.
+        // Vertical cascade: [1 4 6 4 1] = [1 1]^4, so with the rounded rows h_k kept as running pair sums
+        //   p_k = h_k + h_k+1,  v_k = p_k + p_k+1,  q_k = v_k + v_k+1,  o_k = q_k + q_k+1  (= the column sum of output row k+2)
+        // a new row costs 4 additions per packed lane, the state is 4 registers per lane (H = h, P = p, V = v, Q = q of
+        // the newest complete index) and nothing is multiplied.  o reaches 4080 and must be centred to be a half:
+        //   * lanes < kCascadeHalf take the rows as halves (h - 128) u -- the horizontal pass's rounding FMA gives that
+        //     for free with a zero addend (RNE(x) - 128 = RNE(x - 128)) -- so p, v, q, o are exact halves in
+        //     [-2048, 2047] u: 4 HADD2 + the rounding HFMA2, all on the FMA pipe;
+        //   * the other lanes keep byte patterns, add p, v, q (<= 2040: still bit patterns of halves) on the integer ALU
+        //     pipe and centre q with one HADD2: 3 IADD + 2 HADD2 + HFMA2, for the balance between the two pipes.
+        // (The window form before this was 2 IADD + 3 HFMA2/HADD2 + the rounding HFMA2 per lane.)
+        constexpr int NH = kCascadeHalf;
+        Acc8 H, P, V, Q, h;
         Row8 row;
-        auto hpass = [&](const uint8_t* rp, Acc8& h) {
+        auto hpass = [&](const uint8_t* rp, Acc8& o) {
             load_row<PRE, kEvenPrmt5>(rp, row, &p);
-            hgauss5_half<C>(row, h);
+            hgauss5_half<C, NH>(row, o);
         };
-        hpass(colp, h0);
-        hpass(colp + kRowBytes, h1);
-        hpass(colp + 2 * kRowBytes, h2);
-        hpass(colp + 3 * kRowBytes, h3);
+        auto add = [&](int k, uint32_t a, uint32_t b) { return k < NH ? hadd2(a, b) : a + b; };
+        hpass(colp, H);
+        hpass(colp + kRowBytes, h);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { P.v[k] = add(k, H.v[k], h.v[k]); H.v[k] = h.v[k]; }
+        hpass(colp + 2 * kRowBytes, h);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t pn = add(k, H.v[k], h.v[k]);
+            V.v[k] = add(k, P.v[k], pn); P.v[k] = pn; H.v[k] = h.v[k];
+        }
+        hpass(colp + 3 * kRowBytes, h);
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+            const uint32_t pn = add(k, H.v[k], h.v[k]);
+            const uint32_t vn = add(k, P.v[k], pn);
+            const uint32_t qn = add(k, V.v[k], vn);
+            Q.v[k] = k < NH ? qn : hadd2(qn, kHNeg2048u);  // integer lanes keep Q centred
+            V.v[k] = vn; P.v[k] = pn; H.v[k] = h.v[k];
+        }
 #pragma unroll 5
         for (int i = 0; i < nrows; ++i) {
-            hpass(colp + (i + 4) * kRowBytes, h4);
+            hpass(colp + (i + 4) * kRowBytes, h);
             uint32_t res[8];
 #pragma unroll
-            for (int k = 0; k < 8; ++k) res[k] = half_gauss5(h0.v[k] + h4.v[k], h1.v[k] + h3.v[k], h2.v[k]);
+            for (int k = 0; k < 8; ++k) {
+                const uint32_t pn = add(k, H.v[k], h.v[k]);
+                const uint32_t vn = add(k, P.v[k], pn);
+                const uint32_t qn = add(k, V.v[k], vn);
+                res[k] = hfma2(hadd2(Q.v[k], qn), kH16th, kH128u);
+                Q.v[k] = k < NH ? qn : hadd2(qn, kHNeg2048u);
+                V.v[k] = vn; P.v[k] = pn; H.v[k] = h.v[k];
+            }
             put16<CLIP, MAPPED>(dptr + (size_t)i * p.dst.pitch,
                     make_uint4(pack_lo(res[0], res[1]), pack_lo(res[2], res[3]), pack_lo(res[4], res[5]), pack_lo(res[6], res[7])), valid, p);
-            h0 = h1; h1 = h2; h2 = h3; h3 = h4;
         }
     } else if constexpr (op_taps(OP) == 1) {
         // 3-tap Gaussians.  h* hold the horizontal pass of rows i-1, i, i+1.

@@ -25,7 +25,6 @@
 #include <vector>
 
 #include "dip.h"
-#include "jpeg_io.h"
 
 namespace ch = std::chrono;
 namespace fs = std::filesystem;
@@ -115,9 +114,9 @@ static bool read_file(const std::string& path, std::vector<uint8_t>& out) {
     return (bool)in.read(reinterpret_cast<char*>(out.data()), n);
 }
 
-// `image.data` empty + jpeg != nullptr: the pixels are decoded from `jpeg_bytes` directly into the device image.
+// `image.data` empty + jpeg: the pixels are decoded from `jpeg_bytes` directly into the device image.
 static void perform_benchmark(dip_ctx* ctx, const Pnm& image, const std::string& filename, const fs::path& outdir, size_t rounds,
-                              bool sync_every_call, int batch, JpegIo* jpeg, const std::vector<uint8_t>& jpeg_bytes,
+                              bool sync_every_call, int batch, bool jpeg, const std::vector<uint8_t>& jpeg_bytes,
                               const std::string& csv_path, const std::string& tool) {
     const int width = image.w, height = image.h, channels = image.c;
     const size_t frame_bytes = (size_t)width * height * channels;
@@ -129,11 +128,8 @@ static void perform_benchmark(dip_ctx* ctx, const Pnm& image, const std::string&
     CHECK(dip_host_alloc(reinterpret_cast<void**>(&h_out), frame_bytes * batch));
     if (jpeg) {
         // decode on the GPU into frame 0 of the input stack, then replicate / fetch the pixels for the Upload row
-        dip_image_info info;
-        CHECK(dip_image_get_info(d_input, &info));
-        std::string err;
-        if (!jpeg_io_decode(jpeg, jpeg_bytes, info.device_ptr, info.pitch, width, height, &err)) {
-            std::fprintf(stderr, "Error: %s\n", err.c_str());
+        if (dip_jpeg_decode(ctx, jpeg_bytes.data(), jpeg_bytes.size(), d_input, 0) < 0) {
+            std::fprintf(stderr, "Error: %s\n", dip_last_error_string(ctx));
             std::exit(6);
         }
         dip_image* f0 = nullptr;
@@ -170,15 +166,13 @@ static void perform_benchmark(dip_ctx* ctx, const Pnm& image, const std::string&
         std::printf("| %-*s | %10.6fs (once) | %10.6fs (%zu times) |\n", biggest, description.c_str(), once, times, rounds);
         if (prefix.empty()) continue;
         if (jpeg) {  // encode frame 0 of the result on the GPU; only the bitstream comes back
-            dip_image_info info;
-            CHECK(dip_image_get_info(d_output, &info));
-            CHECK(dip_sync(ctx));
-            std::vector<uint8_t> bits;
-            std::string err;
-            if (!jpeg_io_encode(jpeg, info.device_ptr, info.pitch, width, height, &bits, &err)) {
-                std::fprintf(stderr, "Error: %s\n", err.c_str());
+            std::vector<uint8_t> bits(frame_bytes + 65536);
+            size_t len = 0;
+            if (dip_jpeg_encode(ctx, d_output, 0, 95, bits.data(), bits.size(), &len) < 0) {  // imwrite's default quality
+                std::fprintf(stderr, "Error: %s\n", dip_last_error_string(ctx));
                 continue;
             }
+            bits.resize(len);
             std::ofstream out((outdir / (prefix + "-" + filename)).string(), std::ios::binary);   // sycl:374
             out.write(reinterpret_cast<const char*>(bits.data()), (std::streamsize)bits.size());
             continue;
@@ -262,13 +256,12 @@ int main(int argc, char** argv) {
     std::printf("Platform: CUDA sm_%d%d, %d SMs (%s)\n", info.cc_major, info.cc_minor, info.sm_count, dip_version());
 
     Pnm image;
-    JpegIo* jpeg = nullptr;
+    const bool jpeg = has_jpeg_ext(inpath);
     std::vector<uint8_t> jpeg_bytes;
-    if (has_jpeg_ext(inpath)) {
-        std::string err;
-        if (!read_file(inpath.string(), jpeg_bytes) || !(jpeg = jpeg_io_create(&err)) ||
-            !jpeg_io_info(jpeg, jpeg_bytes, &image.w, &image.h, &err)) {                                  // sycl:445-449
-            std::fprintf(stderr, "Error: Failed to load image from '%s' %s\n", inpath.string().c_str(), err.c_str());
+    if (jpeg) {
+        if (!read_file(inpath.string(), jpeg_bytes) ||
+            dip_jpeg_info(ctx, jpeg_bytes.data(), jpeg_bytes.size(), &image.w, &image.h, nullptr) < 0) {  // sycl:445-449
+            std::fprintf(stderr, "Error: Failed to load image from '%s' %s\n", inpath.string().c_str(), dip_last_error_string(ctx));
             return 6;
         }
         image.c = 3;  // cv::imread delivers BGR for JPEG input
@@ -278,7 +271,6 @@ int main(int argc, char** argv) {
     }
     if (!fs::exists(outpath)) fs::create_directories(outpath);                                            // sycl:452-454
     perform_benchmark(ctx, image, inpath.filename().string(), outpath, rounds, sync_every_call, batch, jpeg, jpeg_bytes, csv_path, tool);  // sycl:460
-    jpeg_io_destroy(jpeg);
     dip_shutdown(ctx);
     return 0;
 }

@@ -182,6 +182,44 @@ class Context:
         check(lib().dip_image_wrap(self._h, C.c_void_p(device_ptr), width, height, channels, frames, pitch, frame_stride, C.byref(h)), self._h)
         return Image(self, h.value, parent=keepalive)
 
+    # -- JPEG on the GPU side (cv.imread opencv/benchmark.py:14, cv.imwrite :114) -------------------
+    def jpeg_info(self, data: bytes) -> tuple[int, int, int]:
+        """(width, height, components) of a JPEG byte stream."""
+        w, h, n = C.c_int(), C.c_int(), C.c_int()
+        buf = (C.c_ubyte * len(data)).from_buffer_copy(data)
+        check(lib().dip_jpeg_info(self._h, buf, len(data), C.byref(w), C.byref(h), C.byref(n)), self._h)
+        return w.value, h.value, n.value
+
+    def imdecode(self, streams, dst: Image | None = None, first_frame: int = 0, channels: int = 3) -> Image:
+        """cv.imdecode on the GPU: `streams` (one bytes object or a list of same-sized JPEGs) decoded straight into the
+        frames of a device stack (allocated when `dst` is None).  Only the compressed bytes cross PCIe."""
+        if isinstance(streams, (bytes, bytearray, memoryview)):
+            streams = [bytes(streams)]
+        streams = [bytes(s) for s in streams]
+        if dst is None:
+            w, h, _ = self.jpeg_info(streams[0])
+            dst = self.image(w, h, channels, len(streams))
+        bufs = [(C.c_ubyte * len(s)).from_buffer_copy(s) for s in streams]
+        if len(bufs) == 1:
+            check(lib().dip_jpeg_decode(self._h, bufs[0], len(streams[0]), dst._h, first_frame), self._h)
+        else:
+            ptrs = (C.c_void_p * len(bufs))(*[C.addressof(b) for b in bufs])
+            lens = (C.c_size_t * len(bufs))(*[len(s) for s in streams])
+            check(lib().dip_jpeg_decode_batch(self._h, ptrs, lens, len(bufs), dst._h, first_frame), self._h)
+        self.sync()  # the host copies of the streams are released on return
+        return dst
+
+    def imencode(self, src: Image, frame: int = 0, quality: int = 95) -> bytes:
+        """cv.imencode('.jpg') on the GPU: the bitstream of one frame of a device stack (imwrite's defaults)."""
+        cap = src.width * src.height * src.channels + 65536
+        out = (C.c_ubyte * cap)()
+        n = C.c_size_t()
+        check(lib().dip_jpeg_encode(self._h, src._h, frame, quality, out, cap, C.byref(n)), self._h)
+        return bytes(memoryview(out)[: n.value])
+
+    def jpeg_backend(self) -> str:
+        return lib().dip_jpeg_backend(self._h).decode()
+
     def image_like(self, other: Image) -> Image:
         return self.image(other.width, other.height, other.channels, other.frames)
 

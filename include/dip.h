@@ -118,6 +118,30 @@ DIP_API int dip_download(dip_ctx* ctx, const dip_image* src, uint8_t* host, size
  * vglClCopy vgl:121 */
 DIP_API int dip_copy(dip_ctx* ctx, const dip_image* src, dip_image* dst);
 
+/* ---- JPEG in and out on the GPU side of upload / download ----------------------------------
+ * The reference reads its input with cv.imread (opencv:14, sycl:445) and writes every result with imwrite (opencv:114,
+ * sycl:374).  Here only the compressed bytes cross PCIe: decoding lands the pixels directly in a frame of a device
+ * stack, encoding reads one.  The codec is nvJPEG, bound at run time (DIP_ERR_UNSUPPORTED when libnvjpeg is absent; env
+ * DIP_NVJPEG_LIB names another copy); it is library code around the hot path, not one of this library's kernels, and
+ * JPEG being lossy, a decode agrees with cv.imread's libjpeg-turbo only to within rounding of the inverse DCT and
+ * the chroma upsampling filter (tests compare by PSNR).
+ *   decode: 3-channel images receive interleaved BGR like cv.imread, 1-channel images the luma plane; the stream's size
+ *           must equal the image's.  Stream-ordered on the compute stream: later dip_* calls see the pixels; the host
+ *           bytes must stay valid until the next dip_sync.
+ *   decode_batch: `count` streams into frames [first_frame, first_frame + count): one nvjpegDecodeBatched on the GPU's
+ *           hardware JPEG engines when they accept the streams (baseline Huffman), else on the GPU-assisted backend.
+ *   encode: frame `frame` of a 3-channel image, quality 1..100, 4:2:0 chroma (imwrite's defaults are quality 95,
+ *           4:2:0).  *len = the stream's size; DIP_ERR_NOMEM (with *len set) when `capacity` is too small.
+ *           Synchronous: the bytes are in `out` on return.
+ *   backend: which path the last decode took: "hardware", "gpu-hybrid-batched", "gpu-hybrid" or "none". */
+DIP_API int dip_jpeg_info(dip_ctx* ctx, const uint8_t* data, size_t len, int* width, int* height, int* components);
+DIP_API int dip_jpeg_decode(dip_ctx* ctx, const uint8_t* data, size_t len, dip_image* dst, int frame);
+DIP_API int dip_jpeg_decode_batch(dip_ctx* ctx, const uint8_t* const* data, const size_t* len, int count,
+                                  dip_image* dst, int first_frame);
+DIP_API int dip_jpeg_encode(dip_ctx* ctx, const dip_image* src, int frame, int quality, uint8_t* out,
+                            size_t capacity, size_t* len);
+DIP_API const char* dip_jpeg_backend(const dip_ctx* ctx);
+
 /* ---- point operations ------------------------------------------------------------ */
 /* "Inversion": cv.bitwise_not opencv:95, InvertKernel sycl:54-69, vglClInvert vgl:122 */
 DIP_API int dip_invert(dip_ctx* ctx, const dip_image* src, dip_image* dst);
@@ -352,7 +376,9 @@ DIP_API int dip_flag_read(dip_ctx* ctx, const dip_image* flags, int index, uint3
 /* ---- development hook: kernel-selection knobs for A/B measurements inside one process.
  * keys: "tile_rows" (stencil tile height: 0 = automatic, >= 60 the stack tiles, < 60 the single-image tiles),
  * "no_pad" (1 = do not pad shared memory to limit the resident tiles of the HBM-bound stencils), "int_math" (1 = the
- * packed-integer forms of the separable Gaussians instead of the packed-half ones).  Not needed by applications. */
+ * packed-integer forms of the separable Gaussians instead of the packed-half ones), "umma" (1 = the fused 1x5+5x1
+ * Gaussian on the tensor cores), "direct_generic" (1 = small arbitrary masks on the direct kernel), "fused_shape"
+ * (band shape of the fused Gaussian -> erosion kernel on one-channel images).  Not needed by applications. */
 DIP_API int dip_debug_set(const char* key, int value);
 
 #ifdef __cplusplus

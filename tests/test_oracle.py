@@ -111,6 +111,28 @@ def test_numpy_restatement_of_packed_rounding():
         assert np.array_equal(got, want), s
 
 
+def test_numpy_restatement_of_half_precision_cascade():
+    """The fused 1x5+5x1 Gaussian's vertical pass in IEEE half precision (stencil_tiled.cuh, "vertical cascade"):
+    rows arrive as halves (h - 128) u with u = 2^-24 (the subnormal ulp), [1 4 6 4 1] is four rounds of pairwise sums,
+    every partial sum stays an integer multiple of u in [-2048, 2047] (exact), and one fused multiply-add
+    o * 2^-4 + 128 u rounds to the ulp, i.e. to round-half-even(S / 16) as a byte pattern."""
+    u = np.float16(2.0 ** -24)
+    assert np.array_equal((np.arange(256) * np.float64(u)).astype(np.float16).view(np.uint16), np.arange(256))  # byte b IS b u
+    rng = np.random.default_rng(5)
+    h = rng.integers(0, 256, (5, 200000))
+    h[:, :4] = [[0, 255, 0, 255], [0, 255, 255, 0], [0, 255, 0, 255], [0, 255, 255, 0], [0, 255, 0, 255]]
+    hb = ((h - 128) * np.float64(u)).astype(np.float16)  # what the horizontal pass's rounding FMA leaves with a zero addend
+    p = [hb[k] + hb[k + 1] for k in range(4)]            # numpy adds float16 with IEEE rounding, like HADD2
+    v = [p[k] + p[k + 1] for k in range(3)]
+    q = [v[k] + v[k + 1] for k in range(2)]
+    o = q[0] + q[1]
+    S = h[0] + 4 * h[1] + 6 * h[2] + 4 * h[3] + h[4]
+    assert np.array_equal(o.astype(np.float64) / np.float64(u), S - 2048)  # exact, centred
+    # the rounding FMA: exact product and sum (float64 holds them), ONE rounding to half
+    res = (o.astype(np.float64) / 16 + 128 * np.float64(u)).astype(np.float16).view(np.uint16)
+    assert np.array_equal(res, np.rint(S / 16.0).astype(np.int64))
+
+
 def test_row_addressed_synth_and_checksum_compose(orc):
     """Bands of a mosaic: synth_rows stitches to the whole, band checksums add up to the whole's."""
     whole = orc.synth(64, 50, 1, seed=3, frame=0)

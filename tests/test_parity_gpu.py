@@ -556,6 +556,56 @@ def test_native_cli_driver_jpeg_through_nvjpeg(ctx, dip, orc, tmp_path):
         assert psnr > (18.0 if prefix == "threshold" else 30.0), (prefix, psnr)
 
 
+def _psnr(a, b):
+    mse = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2)
+    return 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
+
+
+def test_jpeg_decode_and_encode_through_the_c_abi(ctx, dip):
+    """dip_jpeg_* (SURVEY 8f rank 2): the reference's input decoded on the GPU straight into device frames -- one call,
+    and a batch into a stack -- agrees with cv.imread (opencv:14) up to decoder rounding; a result encoded on the GPU
+    decodes (cv.imdecode) to the image that was encoded (opencv:114); error paths report instead of crashing."""
+    cv2 = pytest.importorskip("cv2")
+    data = open(os.path.join(ROOT, "data", "fundus.jpg"), "rb").read()
+    want = cv2.imread(os.path.join(ROOT, "data", "fundus.jpg"))
+    assert ctx.jpeg_info(data) == (want.shape[1], want.shape[0], 3)
+    one = ctx.imdecode(data)
+    got = one.download()
+    assert got.shape == want.shape
+    assert _psnr(got, want) > 40.0, _psnr(got, want)       # two IDCT / chroma-upsampling implementations
+    assert np.abs(got.astype(int) - want.astype(int)).max() <= 24
+    stack = ctx.imdecode([data] * 5)
+    assert ctx.jpeg_backend() in ("hardware", "gpu-hybrid-batched", "gpu-hybrid")
+    frames = stack.download()
+    for f in range(5):
+        assert _psnr(frames[f], want) > 40.0, (f, ctx.jpeg_backend())
+    # the decoded frames are ordinary device images: an operation on them equals the operation on the download
+    dst = ctx.image_like(stack)
+    ctx.invert(stack, dst)
+    assert np.array_equal(dst.download(), 255 - frames)
+    # luma only
+    gray = ctx.imdecode(data, channels=1)
+    assert _psnr(gray.download()[:, :, 0], cv2.cvtColor(want, cv2.COLOR_BGR2GRAY)) > 35.0
+    # encode on the GPU, decode on the CPU
+    bits = ctx.imencode(one, quality=95)
+    assert bits[:2] == b"\xff\xd8" and len(bits) < got.size // 4
+    back = cv2.imdecode(np.frombuffer(bits, np.uint8), cv2.IMREAD_COLOR)
+    assert back.shape == got.shape and _psnr(back, got) > 38.0, _psnr(back, got)
+    # errors
+    small = ctx.image(64, 64, 3)
+    with pytest.raises(dip.DipError) as e:
+        ctx.imdecode(data, dst=small)
+    assert e.value.code == -2  # DIP_ERR_SHAPE
+    with pytest.raises(dip.DipError):
+        ctx.imdecode(b"not a jpeg at all", dst=small)
+    four = ctx.image(64, 64, 4)
+    with pytest.raises(dip.DipError) as e:
+        ctx.imencode(four)
+    assert e.value.code == -3  # DIP_ERR_UNSUPPORTED
+    for im in (one, stack, dst, gray, small, four):
+        im.close()
+
+
 @pytest.mark.parametrize("c", [1, 3, 4])
 def test_fused_gauss5x5_erode3x3_equals_the_two_ops(ctx, dip, orc, c):
     """dip_gauss5x5_erode3x3 (one kernel) == filter2D 5x5 then erode 3x3 (opencv:103 then :99), bit for bit."""

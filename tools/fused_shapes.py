@@ -1,0 +1,31 @@
+"""The fused Gaussian 5x5 -> erosion 3x3 kernel on a one-channel mosaic band for several settings of the "fused_shape" knob
+(band rows x warps per CTA, register caps): checksum against the default shape, then ms per launch in the sustained power
+state (0.5 s of launches before the timed ones).  usage: python tools/fused_shapes.py [shape ...]"""
+import os, sys, statistics
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from _dip_pkg import load
+dip = load(); L = dip.lib()
+ctx = dip.Context(0)
+fused = dip.make_op("gauss5x5_erode3x3")
+shapes = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4, 5, 6, 7]
+names = {0: "15 rows x 4 warps (shipped)", 1: "30 x 2", 2: "30 x 4", 3: "15 x 4, 5 CTAs/SM by registers", 4: "15 x 2", 5: "30 x 3", 6: "15 x 4, 6 CTAs/SM by registers", 7: "45 x 2"}
+w, h = 65536, 16384
+src = ctx.image(w, h, 1).synth_fill(seed=1); dst = ctx.image(w, h, 1)
+L.dip_debug_set(b"fused_shape", 0)
+ctx.apply(fused, src, dst)
+want = dst.checksum()
+res = {s: [] for s in shapes}
+for rnd in range(4):
+    for s in shapes:
+        L.dip_debug_set(b"fused_shape", s)
+        ctx.apply(fused, src, dst)
+        assert dst.checksum() == want, f"shape {s} differs"
+        for _ in range(60): ctx.apply(fused, src, dst)
+        ctx.timer_start()
+        for _ in range(20): ctx.apply(fused, src, dst)
+        res[s].append(ctx.timer_stop() / 20)
+print("| fused_shape | ms per 65536x16384 band, min / median | GB/s (2 B/pixel) | fraction of 6459 |")
+print("|---|---|---|---|")
+for s in shapes:
+    t = min(res[s])
+    print(f"| {s}: {names.get(s, '')} | {t:.4f} / {statistics.median(res[s]):.4f} | {2 * w * h / t / 1e6:.0f} | {2 * w * h / t / 1e6 / 6459:.3f} |")
