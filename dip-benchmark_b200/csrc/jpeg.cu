@@ -7,13 +7,24 @@
 //
 // The codec itself is nvJPEG (CUDA toolkit LIBRARY code, not one of this library's kernels, and not part of the
 // operation hot path).  It is bound at run time (dlopen) so that libdip_b200.so has no load-time dependency on it: a
-// box without libnvjpeg gets DIP_ERR_UNSUPPORTED from these four entry points and everything else works.
-// Batches go through nvjpegDecodeBatched, on the hardware JPEG engines (NVJPEG_BACKEND_HARDWARE) when the GPU and the
-// streams allow it (baseline Huffman only), else on the default GPU-assisted backend.
+// box without libnvjpeg gets DIP_ERR_UNSUPPORTED from these entry points and everything else works.
+//
+// Decoding uses nvJPEG's decoupled phases (parse, host, transfer, device) with the GPU_HYBRID decoder -- Huffman
+// decoding on the GPU; what remains on the host is a scan of the bitstream -- and falls back to the HYBRID decoder (CPU
+// Huffman) for streams GPU_HYBRID refuses (progressive ...).  Measured on B200 / nvJPEG 12.4 for the 3504x2336 fundus
+// image (tools/nvjpeg_probe.py): the one-call API nvjpegDecode 26.6 ms whatever backend the handle was created with,
+// decoupled HYBRID 26.5 ms (25.3 of them host Huffman), decoupled GPU_HYBRID 10.4 ms (9.6 host scan, 0.4 device);
+// NVJPEG_BACKEND_HARDWARE is refused (ARCH_MISMATCH): this nvJPEG drives no JPEG engine on sm_100.  The host phase is
+// the cost and it is per image, so a batch is decoded by several host threads, each with its own decoder state, pinned
+// and device buffers and CUDA stream (the nvJPEG handle is thread-safe, states are not); the compute stream is ordered
+// before and after them with events.
 #include <dlfcn.h>
 #include <nvjpeg.h>
 
+#include <algorithm>
+#include <atomic>
 #include <mutex>
+#include <thread>
 
 #include "dip_internal.h"
 
@@ -28,9 +39,25 @@ namespace {
     X(nvjpegJpegStateCreate)             \
     X(nvjpegJpegStateDestroy)            \
     X(nvjpegGetImageInfo)                \
-    X(nvjpegDecode)                      \
-    X(nvjpegDecodeBatchedInitialize)     \
-    X(nvjpegDecodeBatched)               \
+    X(nvjpegDecoderCreate)               \
+    X(nvjpegDecoderDestroy)              \
+    X(nvjpegDecoderStateCreate)          \
+    X(nvjpegBufferPinnedCreate)          \
+    X(nvjpegBufferPinnedDestroy)         \
+    X(nvjpegBufferDeviceCreate)          \
+    X(nvjpegBufferDeviceDestroy)         \
+    X(nvjpegStateAttachPinnedBuffer)     \
+    X(nvjpegStateAttachDeviceBuffer)     \
+    X(nvjpegJpegStreamCreate)            \
+    X(nvjpegJpegStreamDestroy)           \
+    X(nvjpegJpegStreamParse)             \
+    X(nvjpegDecodeParamsCreate)          \
+    X(nvjpegDecodeParamsDestroy)         \
+    X(nvjpegDecodeParamsSetOutputFormat) \
+    X(nvjpegDecoderJpegSupported)        \
+    X(nvjpegDecodeJpegHost)              \
+    X(nvjpegDecodeJpegTransferToDevice)  \
+    X(nvjpegDecodeJpegDevice)            \
     X(nvjpegEncoderStateCreate)          \
     X(nvjpegEncoderStateDestroy)         \
     X(nvjpegEncoderParamsCreate)         \
@@ -76,29 +103,53 @@ const NvjpegApi* nvjpeg_api() {
 
 }  // namespace
 
+// One decoding lane: everything a host thread needs to take streams through the four phases on its own CUDA stream.
+struct JpegLane {
+    nvjpegJpegDecoder_t dec[2] = {nullptr, nullptr};   // [0] GPU_HYBRID, [1] HYBRID
+    nvjpegJpegState_t st[2] = {nullptr, nullptr};
+    nvjpegBufferPinned_t pinned[2] = {nullptr, nullptr};  // alternate between consecutive images of the lane
+    nvjpegBufferDevice_t device = nullptr;
+    nvjpegJpegStream_t stream[2] = {nullptr, nullptr};
+    nvjpegDecodeParams_t params = nullptr;
+    cudaStream_t cuda = nullptr;
+    cudaEvent_t done = nullptr;
+};
+
 // per-ctx codec state, created on first use, released by dip_shutdown (jpeg_release)
 struct JpegState {
-    nvjpegHandle_t handle = nullptr;          // default backend: single decodes, encodes, batched fallback
-    nvjpegJpegState_t state = nullptr;
-    nvjpegHandle_t hw_handle = nullptr;       // NVJPEG_BACKEND_HARDWARE, if the GPU has the engines
-    nvjpegJpegState_t hw_state = nullptr;
-    nvjpegJpegState_t batch_state = nullptr;  // default backend, batched
-    int hw_batch = 0, hw_fmt = -1, def_batch = 0, def_fmt = -1;  // what the batched states are initialised for
+    nvjpegHandle_t handle = nullptr;
+    std::vector<JpegLane*> lanes;
     nvjpegEncoderState_t enc_state = nullptr;
     nvjpegEncoderParams_t enc_params = nullptr;
+    cudaEvent_t ready = nullptr;              // "the compute stream reached the decode call"
     const char* last_backend = "none";
+    int last_lanes = 0;
 };
+
+static void lane_destroy(const NvjpegApi* a, JpegLane* l) {
+    if (!l) return;
+    if (l->cuda) cudaStreamSynchronize(l->cuda);
+    if (l->params) a->nvjpegDecodeParamsDestroy(l->params);
+    for (int i = 0; i < 2; ++i) {
+        if (l->stream[i]) a->nvjpegJpegStreamDestroy(l->stream[i]);
+        if (l->st[i]) a->nvjpegJpegStateDestroy(l->st[i]);
+        if (l->dec[i]) a->nvjpegDecoderDestroy(l->dec[i]);
+        if (l->pinned[i]) a->nvjpegBufferPinnedDestroy(l->pinned[i]);
+    }
+    if (l->device) a->nvjpegBufferDeviceDestroy(l->device);
+    if (l->done) cudaEventDestroy(l->done);
+    if (l->cuda) cudaStreamDestroy(l->cuda);
+    delete l;
+}
 
 void jpeg_release(dip_ctx* ctx) {
     JpegState* s = static_cast<JpegState*>(ctx->jpeg);
     if (!s) return;
     const NvjpegApi* a = nvjpeg_api();
+    for (JpegLane* l : s->lanes) lane_destroy(a, l);
     if (s->enc_params) a->nvjpegEncoderParamsDestroy(s->enc_params);
     if (s->enc_state) a->nvjpegEncoderStateDestroy(s->enc_state);
-    if (s->batch_state) a->nvjpegJpegStateDestroy(s->batch_state);
-    if (s->hw_state) a->nvjpegJpegStateDestroy(s->hw_state);
-    if (s->hw_handle) a->nvjpegDestroy(s->hw_handle);
-    if (s->state) a->nvjpegJpegStateDestroy(s->state);
+    if (s->ready) cudaEventDestroy(s->ready);
     if (s->handle) a->nvjpegDestroy(s->handle);
     delete s;
     ctx->jpeg = nullptr;
@@ -129,19 +180,7 @@ int jpeg_state(dip_ctx* ctx, JpegState** out) {
         JpegState* s = new JpegState();
         ctx->jpeg = s;
         DIP_NVJPEG(ctx, a->nvjpegCreateSimple(&s->handle));
-        DIP_NVJPEG(ctx, a->nvjpegJpegStateCreate(s->handle, &s->state));
-        // the hardware engines are optional: absent on some parts, and refused when the driver has none to give
-        const char* no_hw = getenv("DIP_JPEG_NO_HW");
-        if (!(no_hw && no_hw[0] == '1') &&
-            a->nvjpegCreateEx(NVJPEG_BACKEND_HARDWARE, nullptr, nullptr, NVJPEG_FLAGS_DEFAULT, &s->hw_handle) == NVJPEG_STATUS_SUCCESS) {
-            if (a->nvjpegJpegStateCreate(s->hw_handle, &s->hw_state) != NVJPEG_STATUS_SUCCESS) {
-                a->nvjpegDestroy(s->hw_handle);
-                s->hw_handle = nullptr;
-                s->hw_state = nullptr;
-            }
-        } else {
-            s->hw_handle = nullptr;
-        }
+        DIP_CUDA(ctx, cudaEventCreateWithFlags(&s->ready, cudaEventDisableTiming));
     }
     *out = static_cast<JpegState*>(ctx->jpeg);
     return DIP_OK;
@@ -160,6 +199,40 @@ int order_after_copies(dip_ctx* ctx, const dip_image* img) {
     const dip_image* root = root_of(const_cast<dip_image*>(img));
     if (root->copy_pending && root->copy_done) DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, root->copy_done, 0));
     dep_touch(ctx);
+    return DIP_OK;
+}
+
+int lane_create(dip_ctx* ctx, JpegState* s, JpegLane** out) {
+    const NvjpegApi* a = nvjpeg_api();
+    JpegLane* l = new JpegLane();
+    auto bail = [&](int rc) { lane_destroy(a, l); return rc; };
+#define DIP_LANE(expr)                                                              \
+    do {                                                                            \
+        nvjpegStatus_t _s = (expr);                                                 \
+        if (_s != NVJPEG_STATUS_SUCCESS) return bail(nvfail(ctx, _s, #expr));       \
+    } while (0)
+    if (cudaStreamCreateWithFlags(&l->cuda, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&l->done, cudaEventDisableTiming) != cudaSuccess)
+        return bail(fail(ctx, DIP_ERR_CUDA, "dip_jpeg_decode: cannot create a lane's stream"));
+    // GPU_HYBRID is optional (DIP_JPEG_CPU_HUFFMAN=1 skips it: A/B), HYBRID is the fallback every stream can take
+    const char* cpu_only = getenv("DIP_JPEG_CPU_HUFFMAN");
+    if (!(cpu_only && cpu_only[0] == '1') && a->nvjpegDecoderCreate(s->handle, NVJPEG_BACKEND_GPU_HYBRID, &l->dec[0]) == NVJPEG_STATUS_SUCCESS) {
+        if (a->nvjpegDecoderStateCreate(s->handle, l->dec[0], &l->st[0]) != NVJPEG_STATUS_SUCCESS) {
+            a->nvjpegDecoderDestroy(l->dec[0]);
+            l->dec[0] = nullptr;
+        }
+    } else {
+        l->dec[0] = nullptr;
+    }
+    DIP_LANE(a->nvjpegDecoderCreate(s->handle, NVJPEG_BACKEND_HYBRID, &l->dec[1]));
+    DIP_LANE(a->nvjpegDecoderStateCreate(s->handle, l->dec[1], &l->st[1]));
+    for (int i = 0; i < 2; ++i) {
+        DIP_LANE(a->nvjpegBufferPinnedCreate(s->handle, nullptr, &l->pinned[i]));
+        DIP_LANE(a->nvjpegJpegStreamCreate(s->handle, &l->stream[i]));
+    }
+    DIP_LANE(a->nvjpegBufferDeviceCreate(s->handle, nullptr, &l->device));
+    DIP_LANE(a->nvjpegDecodeParamsCreate(s->handle, &l->params));
+#undef DIP_LANE
+    *out = l;
     return DIP_OK;
 }
 
@@ -188,20 +261,9 @@ int dip_jpeg_info(dip_ctx* ctx, const uint8_t* data, size_t len, int* width, int
 }
 
 int dip_jpeg_decode(dip_ctx* ctx, const uint8_t* data, size_t len, dip_image* dst, int frame) {
-    JpegState* s = nullptr;
-    int rc = jpeg_state(ctx, &s);
-    if (rc != DIP_OK) return rc;
-    if ((rc = check_target(ctx, dst, frame, 1, "dip_jpeg_decode")) != DIP_OK) return rc;
-    int w = 0, h = 0;
-    if ((rc = dip_jpeg_info(ctx, data, len, &w, &h, nullptr)) != DIP_OK) return rc;
-    if (w != dst->v.width || h != dst->v.height) return fail(ctx, DIP_ERR_SHAPE, "dip_jpeg_decode: the stream is %dx%d, the image %dx%d", w, h, dst->v.width, dst->v.height);
-    if ((rc = order_after_copies(ctx, dst)) != DIP_OK) return rc;
-    nvjpegImage_t out{};
-    out.channel[0] = dst->v.base + (size_t)frame * dst->v.frame_stride;
-    out.pitch[0] = dst->v.pitch;
-    DIP_NVJPEG(ctx, nvjpeg_api()->nvjpegDecode(s->handle, s->state, data, len, dst->v.channels == 3 ? NVJPEG_OUTPUT_BGRI : NVJPEG_OUTPUT_Y, &out, ctx->compute));
-    s->last_backend = "gpu-hybrid";
-    return DIP_OK;
+    const uint8_t* datas[1] = {data};
+    const size_t lens[1] = {len};
+    return dip_jpeg_decode_batch(ctx, datas, lens, 1, dst, frame);
 }
 
 int dip_jpeg_decode_batch(dip_ctx* ctx, const uint8_t* const* data, const size_t* len, int count, dip_image* dst, int first_frame) {
@@ -211,53 +273,78 @@ int dip_jpeg_decode_batch(dip_ctx* ctx, const uint8_t* const* data, const size_t
     if (!data || !len) return fail(ctx, DIP_ERR_ARG, "dip_jpeg_decode_batch: null stream table");
     if ((rc = check_target(ctx, dst, first_frame, count, "dip_jpeg_decode_batch")) != DIP_OK) return rc;
     if (count == 0) return DIP_OK;
-    const NvjpegApi* a = nvjpeg_api();
     for (int i = 0; i < count; ++i) {
         int w = 0, h = 0;
         if ((rc = dip_jpeg_info(ctx, data[i], len[i], &w, &h, nullptr)) != DIP_OK) return rc;
-        if (w != dst->v.width || h != dst->v.height) return fail(ctx, DIP_ERR_SHAPE, "dip_jpeg_decode_batch: stream %d is %dx%d, the image %dx%d", i, w, h, dst->v.width, dst->v.height);
+        if (w != dst->v.width || h != dst->v.height) return fail(ctx, DIP_ERR_SHAPE, "dip_jpeg_decode: stream %d is %dx%d, the image %dx%d", i, w, h, dst->v.width, dst->v.height);
     }
+    // lanes = host threads of this call
+    int want = (int)std::thread::hardware_concurrency();
+    if (const char* e = getenv("DIP_JPEG_THREADS")) want = atoi(e);
+    want = std::max(1, std::min({want, count, 32}));
+    while ((int)s->lanes.size() < want) {
+        JpegLane* l = nullptr;
+        if ((rc = lane_create(ctx, s, &l)) != DIP_OK) return rc;
+        s->lanes.push_back(l);
+    }
+    // the lanes' streams start after everything enqueued on the compute stream so far (kernels still reading the frames)
     if ((rc = order_after_copies(ctx, dst)) != DIP_OK) return rc;
+    DIP_CUDA(ctx, cudaEventRecord(s->ready, ctx->compute));
     const nvjpegOutputFormat_t fmt = dst->v.channels == 3 ? NVJPEG_OUTPUT_BGRI : NVJPEG_OUTPUT_Y;
-    std::vector<nvjpegImage_t> outs((size_t)count);
-    for (int i = 0; i < count; ++i) {
-        outs[i] = nvjpegImage_t{};
-        outs[i].channel[0] = dst->v.base + (size_t)(first_frame + i) * dst->v.frame_stride;
-        outs[i].pitch[0] = dst->v.pitch;
+    std::atomic<int> next{0};
+    std::atomic<int> used_cpu_huffman{0};
+    std::vector<nvjpegStatus_t> status((size_t)want, NVJPEG_STATUS_SUCCESS);
+    std::vector<cudaError_t> cuda_status((size_t)want, cudaSuccess);
+    const NvjpegApi* a = nvjpeg_api();
+    auto work = [&](int t) {
+        JpegLane* l = s->lanes[(size_t)t];
+        cudaSetDevice(ctx->device);
+        cudaError_t ce = cudaStreamWaitEvent(l->cuda, s->ready, 0);
+        nvjpegStatus_t st = a->nvjpegDecodeParamsSetOutputFormat(l->params, fmt);
+        for (int n = 0; st == NVJPEG_STATUS_SUCCESS && ce == cudaSuccess; ++n) {
+            const int i = next.fetch_add(1);
+            if (i >= count) break;
+            const int slot = n & 1;
+            nvjpegImage_t out{};
+            out.channel[0] = dst->v.base + (size_t)(first_frame + i) * dst->v.frame_stride;
+            out.pitch[0] = dst->v.pitch;
+            if ((st = a->nvjpegJpegStreamParse(s->handle, data[i], len[i], 0, 0, l->stream[slot])) != NVJPEG_STATUS_SUCCESS) break;
+            int unsupported = 1;
+            int d = 0;  // GPU_HYBRID when it takes the stream
+            if (!l->dec[0] || a->nvjpegDecoderJpegSupported(l->dec[0], l->stream[slot], l->params, &unsupported) != NVJPEG_STATUS_SUCCESS || unsupported) {
+                d = 1;
+                used_cpu_huffman.fetch_add(1);
+            }
+            // the pinned buffer of this slot was last read by the transfer of image n - 2 of this lane; the device buffer
+            // and the state by image n - 1's device phase: wait for the lane's stream (0.2-0.7 ms of device work against
+            // 10-25 ms of host work per image, so this never actually waits)
+            if (n > 0 && (ce = cudaStreamSynchronize(l->cuda)) != cudaSuccess) break;
+            if ((st = a->nvjpegStateAttachPinnedBuffer(l->st[d], l->pinned[slot])) != NVJPEG_STATUS_SUCCESS) break;
+            if ((st = a->nvjpegStateAttachDeviceBuffer(l->st[d], l->device)) != NVJPEG_STATUS_SUCCESS) break;
+            if ((st = a->nvjpegDecodeJpegHost(s->handle, l->dec[d], l->st[d], l->params, l->stream[slot])) != NVJPEG_STATUS_SUCCESS) break;
+            if ((st = a->nvjpegDecodeJpegTransferToDevice(s->handle, l->dec[d], l->st[d], l->stream[slot], l->cuda)) != NVJPEG_STATUS_SUCCESS) break;
+            if ((st = a->nvjpegDecodeJpegDevice(s->handle, l->dec[d], l->st[d], &out, l->cuda)) != NVJPEG_STATUS_SUCCESS) break;
+        }
+        if (ce == cudaSuccess) ce = cudaEventRecord(l->done, l->cuda);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(l->cuda);  // the caller's bytes are released when the call returns
+        status[(size_t)t] = st;
+        cuda_status[(size_t)t] = ce;
+    };
+    if (want == 1) {
+        work(0);
+    } else {
+        std::vector<std::thread> threads;
+        for (int t = 1; t < want; ++t) threads.emplace_back(work, t);
+        work(0);
+        for (auto& th : threads) th.join();
     }
-    // 1. the hardware engines (baseline streams only; anything they refuse falls through)
-    if (s->hw_handle) {
-        bool ok = true;
-        if (s->hw_batch != count || s->hw_fmt != (int)fmt) {
-            ok = a->nvjpegDecodeBatchedInitialize(s->hw_handle, s->hw_state, count, 1, fmt) == NVJPEG_STATUS_SUCCESS;
-            s->hw_batch = ok ? count : 0;
-            s->hw_fmt = (int)fmt;
-        }
-        if (ok && a->nvjpegDecodeBatched(s->hw_handle, s->hw_state, data, len, outs.data(), ctx->compute) == NVJPEG_STATUS_SUCCESS) {
-            s->last_backend = "hardware";
-            return DIP_OK;
-        }
-        s->hw_batch = 0;
+    for (int t = 0; t < want; ++t) {
+        if (cuda_status[(size_t)t] != cudaSuccess) return fail_cuda(ctx, cuda_status[(size_t)t], "dip_jpeg_decode (lane stream)", __FILE__, __LINE__);
+        if (status[(size_t)t] != NVJPEG_STATUS_SUCCESS) return nvfail(ctx, status[(size_t)t], "dip_jpeg_decode (decoupled nvJPEG phase)");
+        DIP_CUDA(ctx, cudaStreamWaitEvent(ctx->compute, s->lanes[(size_t)t]->done, 0));  // later dip_* calls see the pixels
     }
-    // 2. the default backend, batched
-    if (!s->batch_state && a->nvjpegJpegStateCreate(s->handle, &s->batch_state) != NVJPEG_STATUS_SUCCESS) s->batch_state = nullptr;
-    if (s->batch_state) {
-        bool ok = true;
-        if (s->def_batch != count || s->def_fmt != (int)fmt) {
-            ok = a->nvjpegDecodeBatchedInitialize(s->handle, s->batch_state, count, 1, fmt) == NVJPEG_STATUS_SUCCESS;
-            s->def_batch = ok ? count : 0;
-            s->def_fmt = (int)fmt;
-        }
-        if (ok && a->nvjpegDecodeBatched(s->handle, s->batch_state, data, len, outs.data(), ctx->compute) == NVJPEG_STATUS_SUCCESS) {
-            s->last_backend = "gpu-hybrid-batched";
-            return DIP_OK;
-        }
-        s->def_batch = 0;
-    }
-    // 3. one by one
-    for (int i = 0; i < count; ++i)
-        DIP_NVJPEG(ctx, a->nvjpegDecode(s->handle, s->state, data[i], len[i], fmt, &outs[i], ctx->compute));
-    s->last_backend = "gpu-hybrid";
+    s->last_backend = used_cpu_huffman.load() == 0 ? "gpu-huffman" : used_cpu_huffman.load() == count ? "cpu-huffman" : "mixed";
+    s->last_lanes = want;
     return DIP_OK;
 }
 

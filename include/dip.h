@@ -126,14 +126,16 @@ DIP_API int dip_copy(dip_ctx* ctx, const dip_image* src, dip_image* dst);
  * JPEG being lossy, a decode agrees with cv.imread's libjpeg-turbo only to within rounding of the inverse DCT and
  * the chroma upsampling filter (tests compare by PSNR).
  *   decode: 3-channel images receive interleaved BGR like cv.imread, 1-channel images the luma plane; the stream's size
- *           must equal the image's.  Stream-ordered on the compute stream: later dip_* calls see the pixels; the host
- *           bytes must stay valid until the next dip_sync.
- *   decode_batch: `count` streams into frames [first_frame, first_frame + count): one nvjpegDecodeBatched on the GPU's
- *           hardware JPEG engines when they accept the streams (baseline Huffman), else on the GPU-assisted backend.
+ *           must equal the image's.  Ordered on the compute stream on both sides (it runs after what was enqueued
+ *           before, later dip_* calls see the pixels); the host bytes are free again when the call returns.  Huffman
+ *           decoding runs on the GPU (nvJPEG's GPU_HYBRID decoder; CPU Huffman for streams it refuses: progressive).
+ *   decode_batch: `count` streams into frames [first_frame, first_frame + count), decoded by up to
+ *           min(count, host cores, 32) host threads (env DIP_JPEG_THREADS), each with its own decoder state and CUDA
+ *           stream: the per-image host phase (a scan of the bitstream) is what limits a decode, not the GPU.
  *   encode: frame `frame` of a 3-channel image, quality 1..100, 4:2:0 chroma (imwrite's defaults are quality 95,
  *           4:2:0).  *len = the stream's size; DIP_ERR_NOMEM (with *len set) when `capacity` is too small.
  *           Synchronous: the bytes are in `out` on return.
- *   backend: which path the last decode took: "hardware", "gpu-hybrid-batched", "gpu-hybrid" or "none". */
+ *   backend: where the last decode call's Huffman decoding ran: "gpu-huffman", "cpu-huffman", "mixed" or "none". */
 DIP_API int dip_jpeg_info(dip_ctx* ctx, const uint8_t* data, size_t len, int* width, int* height, int* components);
 DIP_API int dip_jpeg_decode(dip_ctx* ctx, const uint8_t* data, size_t len, dip_image* dst, int frame);
 DIP_API int dip_jpeg_decode_batch(dip_ctx* ctx, const uint8_t* const* data, const size_t* len, int count,
