@@ -25,6 +25,7 @@ Prints ONE JSON line on rank 0.
 from __future__ import annotations
 
 import argparse
+import faulthandler
 import glob
 import json
 import math
@@ -46,6 +47,15 @@ ALG_BYTES_PER_FRAME_OP = 2 * FRAME_BYTES  # read every input byt
 METRIC = "mpixel_per_s_full_op_chain_3504x2336_rgb_u8_batch"
 UNIT = "Mpixel/s"
 NVLINK_PEER_COPY_GBS = 770.0        # B200_PROFILING.md: measured peer copy per direction on this pool
+
+
+def leg(name: str, limit_s: int = 240) -> None:
+    """Progress line on stderr and a watchdog: a leg that does not finish within `limit_s` dumps every thread's stack and
+    ends the process (torchrun then ends the other ranks), so a multi-rank protocol bug costs minutes, not the box."""
+    faulthandler.cancel_dump_traceback_later()
+    if name != "done":
+        faulthandler.dump_traceback_later(limit_s, exit=True)
+    print(f"[bench rank {os.environ.get('RANK', '0')} {time.strftime('%H:%M:%S')}] {name}", file=sys.stderr, flush=True)
 
 
 def measured_peak() -> tuple[float, str]:
@@ -291,6 +301,16 @@ def dist_setup(n_gpus: int):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1 and os.environ.get("DIP_BENCH_SHARE_GPUS") == "1":
+        # development only: more ranks than GPUs (ranks share devices, gloo for the plumbing) to exercise the multi-rank
+        # protocols of an 8-GPU run on a small box; the times of such a run mean nothing
+        import torch
+        import torch.distributed as dist
+        local = local % torch.cuda.device_count()
+        torch.cuda.set_device(local)
+        dist.init_process_group("gloo")
+        dist.barrier()
+        return world, rank, local, dist, torch
     if world > 1:
         # NCCL prints its version banner to stdout when the communicator is created (these boxes export
         # NCCL_DEBUG=VERSION); stdout must carry the JSON line only, so file descriptor 1 points at stderr
@@ -329,7 +349,7 @@ class Ranks:
     def _reduce(self, x: float, op) -> float:
         if self.dist is None:
             return x
-        t = self.torch.tensor([x], dtype=self.torch.float64, device="cuda")
+        t = self.torch.tensor([x], dtype=self.torch.float64, device="cpu" if self.dist.get_backend() == "gloo" else "cuda")
         self.dist.all_reduce(t, op=op)
         return float(t.item())
 
@@ -491,6 +511,7 @@ def mosaic_leg(args, ctx, dip, rk: Ranks, world: int, rank: int, peak: float) ->
     n_m = side * side
 
     def run(name: str, fused: bool, halo: str, iterate: bool = False) -> dict:
+        leg(f"mosaic: {name[:40]}")
         band = dip.mosaic.MosaicBand(ctx, side, side, world, rank, fused=fused, halo=halo, iterate=iterate)
         band.fill_synthetic(seed=0)
         ctx.sync()
@@ -503,20 +524,25 @@ def mosaic_leg(args, ctx, dip, rk: Ranks, world: int, rank: int, peak: float) ->
             cs2 = sum(rk.gather(band.checksum())) & 0xFFFFFFFFFFFFFFFF
             out["checksum_after_2_steps"] = f"{cs2:016x}"
             out["kat_match"] = (kat.get(f"{side}_iter2") == f"{cs2:016x}") if f"{side}_iter2" in kat else None
-        # warm up into the sustained power state, estimate the step time, then time >= min_timed_s
-        t_w = time.time()
-        n = 0
-        while n < 3 or time.time() - t_w < 0.3:
-            band.step()
-            n += 1
-            if n % 16 == 0:
-                ctx.sync()
+        # Every rank runs the SAME number of steps in every phase (the counts come from times that are maxima over the
+        # ranks): with iterate=True a rank may be at most one step ahead of its neighbours, so a rank that stopped earlier
+        # than its neighbour would leave that neighbour's last step waiting for a flag that never comes.
+        def run_steps(n: int):
+            for i in range(n):
+                band.step()
+                if (i + 1) % 64 == 0:
+                    ctx.sync()   # bounds the work queued on the stream
+
         rk.barrier()
         ctx.timer_start()
-        for _ in range(8):
-            band.step()
+        run_steps(8)
         est = rk.max(ctx.timer_stop()) / 8
-        steps = max(8, int(math.ceil(args.mosaic_timed_s * 1e3 / est / 8.0)) * 8)   # the same count on every rank (est is the max over ranks)
+        run_steps(max(8, int(math.ceil(0.3e3 / est / 8.0)) * 8))   # ~0.3 s into the sustained power state
+        rk.barrier()
+        ctx.timer_start()
+        run_steps(8)
+        est = rk.max(ctx.timer_stop()) / 8
+        steps = max(8, int(math.ceil(args.mosaic_timed_s * 1e3 / est / 8.0)) * 8)
         rk.barrier()
         launches0 = ctx.launch_count()
         ctx.timer_start()
@@ -649,21 +675,26 @@ def run_ours(args) -> None:
     src = ctx.image(W, H, C, frames=count).synth_fill(seed=0, first_frame=first)
     dst = ctx.image(W, H, C, frames=count)
     ctx.sync()
+    leg("batch leg")
     b = batch_leg(args, ctx, dip, rk, world, rank, local, count, src, dst, ops, peak, peak_src)
 
     e2e = e2e_chain = fabric = None
     if not args.no_e2e:
+        leg("end-to-end legs")
         e2e, e2e_chain, fabric = e2e_legs(args, ctx, dip, rk, world, count, src, ops)
     src.close(); dst.close()
 
     mosaic = None
     if not args.no_mosaic:
+        leg("mosaic leg")
         mosaic = mosaic_leg(args, ctx, dip, rk, world, rank, peak)
 
     single = None
+    leg("single-image leg")
     if rank == 0 and not args.no_single:
         single = per_op_single_leg(args, ctx, dip, ops, peak)
     rk.barrier()
+    leg("cpu baseline", 600)
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -697,6 +728,7 @@ def run_ours(args) -> None:
             "checksum": b["checksum"],
         }
         print(json.dumps(line))
+    leg("done")
     ctx.close()
     if dist is not None:
         dist.destroy_process_group()
