@@ -66,6 +66,13 @@ int begin_op(dip_ctx* ctx, const dip_image* src, dip_image* dst) {
     return DIP_OK;
 }
 
+static bool dep_conflict_ranges(const DepRange* a, int na, const DepRange* r, int n) {
+    for (int j = 0; j < na; ++j)
+        for (int i = 0; i < n; ++i)
+            if ((a[j].write || r[i].write) && a[j].lo < r[i].hi && r[i].lo < a[j].hi) return true;
+    return false;
+}
+
 static bool dep_conflict(const std::vector<DepRange>& set, const DepRange* r, int n) {
     for (const DepRange& a : set)
         for (int i = 0; i < n; ++i)
@@ -73,14 +80,80 @@ static bool dep_conflict(const std::vector<DepRange>& set, const DepRange* r, in
     return false;
 }
 
+// ---- recording: data-dependency edges (CaptureTracker, dip_internal.h) -----------------------------------------
+// the node of the launch planned last: after a kernel launch the stream's capture dependencies are exactly that node
+static void capture_collect(dip_ctx* ctx) {
+    CaptureTracker& c = ctx->cap;
+    if (c.pending_n < 0) return;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    const cudaGraphNode_t* deps = nullptr;
+    size_t nd = 0;
+    if (cudaStreamGetCaptureInfo_v3(ctx->compute, &st, nullptr, nullptr, &deps, nullptr, &nd) == cudaSuccess &&
+        st == cudaStreamCaptureStatusActive && nd == 1) {
+        CaptureNode cn{};
+        cn.node = deps[0];
+        cn.n = c.pending_n;
+        for (int i = 0; i < c.pending_n; ++i) cn.r[i] = c.pending[i];
+        c.nodes.push_back(cn);
+    } else {
+        cudaGetLastError();
+        c.barrier = true;   // unknown state: the next kernel keeps whatever the stream depends on
+    }
+    c.pending_n = -1;
+}
+
+int capture_join(dip_ctx* ctx) {
+    CaptureTracker& c = ctx->cap;
+    capture_collect(ctx);
+    if (!c.nodes.empty()) {
+        std::vector<cudaGraphNode_t> all;
+        for (const CaptureNode& cn : c.nodes) all.push_back(cn.node);
+        DIP_CUDA(ctx, cudaStreamUpdateCaptureDependencies(ctx->compute, all.data(), all.size(), cudaStreamAddCaptureDependencies));
+        c.nodes.clear();
+    }
+    c.barrier = true;
+    return DIP_OK;
+}
+
+static LaunchMode plan_capture(dip_ctx* ctx, const DepRange* ranges, int n) {
+    CaptureTracker& c = ctx->cap;
+    capture_collect(ctx);
+    ctx->dep.touched = false;
+    constexpr size_t kCap = 64;   // a join now and then keeps the search small
+    if (c.barrier || n <= 0 || n > 2 || c.nodes.size() >= kCap) {
+        // depends on everything recorded so far (and on what the stream itself depends on: a non-kernel node)
+        if (!c.nodes.empty()) {
+            std::vector<cudaGraphNode_t> all;
+            for (const CaptureNode& cn : c.nodes) all.push_back(cn.node);
+            if (cudaStreamUpdateCaptureDependencies(ctx->compute, all.data(), all.size(), cudaStreamAddCaptureDependencies) != cudaSuccess) cudaGetLastError();
+            c.nodes.clear();
+        }
+        c.barrier = false;
+        c.pending_n = 0;          // it stands for everything before it
+        return kFull;
+    }
+    std::vector<cudaGraphNode_t> deps;
+    for (const CaptureNode& cn : c.nodes)
+        if (cn.n == 0 || dep_conflict_ranges(cn.r, cn.n, ranges, n)) deps.push_back(cn.node);
+    c.pending_n = n;
+    for (int i = 0; i < n; ++i) c.pending[i] = ranges[i];
+    const bool only_prev = deps.size() == 1 && !c.nodes.empty() && deps[0] == c.nodes.back().node;
+    if (only_prev) return pdl_enabled() ? kPdlWait : kFull;   // the stream's own dependency, with its early-launch edge
+    if (cudaStreamUpdateCaptureDependencies(ctx->compute, deps.empty() ? nullptr : deps.data(), deps.size(), cudaStreamSetCaptureDependencies) != cudaSuccess) {
+        cudaGetLastError();       // keep the stream's order instead
+        return kFull;
+    }
+    return kFull;
+}
+
 LaunchMode plan_launch(dip_ctx* ctx, const DepRange* ranges, int n) {
+    if (ctx->capturing) return plan_capture(ctx, ranges, n);
     DepTracker& d = ctx->dep;
     static const DepRange everything{0, ~(uintptr_t)0, true};
     if (n <= 0) { ranges = &everything; n = 1; }
     const bool touched = d.touched;
     d.touched = false;
-    // inside a graph recording the stream's in-order completion does not exist (edges are per node): always wait
-    const bool may_skip = pdl_enabled() && !ctx->capturing && !touched && !d.guaranteed.empty();
+    const bool may_skip = pdl_enabled() && !touched && !d.guaranteed.empty();
     constexpr size_t kCap = 24;   // a full launch now and then keeps the sets (and the search) small
     if (d.guaranteed.size() + d.unsafe.size() + (size_t)n <= kCap && !dep_conflict(d.unsafe, ranges, n)) {
         if (may_skip && !dep_conflict(d.guaranteed, ranges, n)) {
@@ -627,7 +700,8 @@ int dip_download(dip_ctx* ctx, const dip_image* src_c, uint8_t* host, size_t hos
 // ---- CUDA graphs: record a sequence of operations once, replay it with one launch ---------------------------
 // The reference's harness enqueues the same few-microsecond kernel thousands of times (measure_time, opencv:33-35 /
 // sycl:33-37); replayed from a graph the host cost of a call drops from ~4-11 us to the graph launch divided by the
-// operations in it, and the kernels keep their programmatic-dependent-launch edges.
+// operations in it.  The nodes' edges are the data dependencies between the recorded kernels (plan_capture above), not
+// the order of the calls.
 int dip_graph_begin(dip_ctx* ctx) {
     if (!ctx) return fail(nullptr, DIP_ERR_ARG, "ctx is null");
     if (ctx->capturing) return fail(ctx, DIP_ERR_ARG, "a graph is already being recorded on this ctx");
@@ -635,6 +709,7 @@ int dip_graph_begin(dip_ctx* ctx) {
     if (rc != DIP_OK) return rc;
     dep_touch(ctx);
     DIP_CUDA(ctx, cudaStreamBeginCapture(ctx->compute, cudaStreamCaptureModeThreadLocal));
+    ctx->cap = CaptureTracker{};
     ctx->capturing = true;
     ctx->capture_launches0 = ctx->launches;
     return DIP_OK;
@@ -644,7 +719,9 @@ int dip_graph_end(dip_ctx* ctx, dip_graph** out) {
     if (!ctx || !out) return fail(ctx, DIP_ERR_ARG, "null argument");
     *out = nullptr;
     if (!ctx->capturing) return fail(ctx, DIP_ERR_ARG, "dip_graph_begin was not called");
+    capture_join(ctx);   // the end of the recording depends on every branch
     ctx->capturing = false;
+    ctx->cap = CaptureTracker{};
     dep_touch(ctx);
     ctx->dep.unsafe.clear();
     ctx->dep.guaranteed.clear();   // what was recorded did not run

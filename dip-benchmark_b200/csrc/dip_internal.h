@@ -81,6 +81,24 @@ struct DepTracker {
     bool touched = true;   // something other than a tracked kernel launch was enqueued on the compute stream since
 };
 
+// While a graph is being recorded (dip_graph_begin .. dip_graph_end) the kernels become nodes whose edges are the DATA
+// dependencies between them, not the order of the calls: an operation depends on exactly the recorded kernels whose
+// byte ranges it conflicts with (read-after-write, write-after-read, write-after-write).  Independent calls -- the
+// reference's loop over a ring of images -- become parallel branches of the graph, so their tails and ramps overlap on
+// replay just as the no-wait launches overlap them on a stream.  An operation that depends on nothing but the kernel
+// recorded right before it keeps the programmatic (early-launch) edge the stream capture gives it.
+struct CaptureNode {
+    cudaGraphNode_t node;
+    DepRange r[2];
+    int n;               // 0: touches memory the tracker knows nothing about (conflicts with everything)
+};
+struct CaptureTracker {
+    std::vector<CaptureNode> nodes;   // recorded kernels a later operation may have to depend on
+    DepRange pending[2];
+    int pending_n = -1;               // ranges of the last planned launch whose node has not been looked up yet (-1: none)
+    bool barrier = false;             // something other than a tracked kernel was recorded: the next kernel keeps the stream's own dependencies
+};
+
 }  // namespace dip
 
 struct dip_graph {
@@ -121,6 +139,7 @@ struct dip_ctx {
     dip_image* scratch[2] = {nullptr, nullptr};
     dip::DepTracker dep;
     bool capturing = false;              // between dip_graph_begin and dip_graph_end: kernels are recorded, not run
+    dip::CaptureTracker cap;
     uint64_t capture_launches0 = 0;
     void* jpeg = nullptr;                // jpeg.cu's codec state (nvJPEG handles), created on first use
     std::string last_error;
@@ -159,7 +178,12 @@ inline bool pdl_enabled() {
 // updates the tracker; the caller passes `mode != kNoWait` to the kernel as its wait flag.
 LaunchMode plan_launch(dip_ctx* ctx, const DepRange* ranges, int n);
 // a non-kernel operation is about to be enqueued on the compute stream (event, wait, copy, memset, graph launch)
-inline void dep_touch(dip_ctx* ctx) { ctx->dep.touched = true; }
+// While recording: everything recorded so far becomes a dependency of it (capture_join).
+int capture_join(dip_ctx* ctx);
+inline void dep_touch(dip_ctx* ctx) {
+    ctx->dep.touched = true;
+    if (ctx->capturing) capture_join(ctx);
+}
 inline DepRange dep_range(const ImgView& v, bool write) {
     const uintptr_t lo = reinterpret_cast<uintptr_t>(v.base);
     return DepRange{lo, lo + v.frame_stride * (size_t)(v.frames - 1) + v.pitch * (size_t)v.height, write};

@@ -284,7 +284,9 @@ DIP_API int dip_run_chain_host(dip_ctx* ctx, const uint8_t* host_in, int width, 
  *      dip_graph_end enqueue on the compute stream -- any dip_* operation, chain or row-band call; not transfers, not
  *      dip_sync -- and replay it with ONE launch per dip_graph_launch.  The reference's measure_time loops
  *      (opencv:33-35, sycl:33-37) enqueue thousands of identical few-microsecond kernels; recorded in blocks, their host
- *      cost per call drops to the graph launch divided by the block size.  The images used while recording must stay
+ *      cost per call drops to the graph launch divided by the block size.  The graph's edges are the data dependencies
+ *      between the recorded kernels (overlapping byte ranges of their operands), not the order of the calls, so
+ *      independent operations overlap on replay.  The images used while recording must stay
  *      alive (and keep their contents' meaning) for every replay; a chain's scratch stack must exist (run it once). */
 typedef struct dip_graph dip_graph;
 DIP_API int dip_graph_begin(dip_ctx* ctx);

@@ -1094,6 +1094,67 @@ def test_independent_calls_overlap_and_dependent_ones_wait(ctx, dip, orc):
             im.close()
 
 
+def test_recorded_random_programs_replay_like_the_cpu(ctx, dip, orc):
+    """A recording turns the calls into a graph whose edges are the DATA dependencies between the kernels (independent
+    calls become parallel branches, plan_capture in context.cu).  Random programs over a pool of images -- reads after
+    writes, writes after reads, writes after writes, in-place point ops, a chain, more kernels than the tracker's window --
+    recorded once and replayed on fresh inputs must give what the same program gives on the CPU, every time."""
+    rng = np.random.default_rng(77)
+    h, w, c = 700, 1500, 3
+    ops = {
+        "invert": (lambda s, d: ctx.invert(s, d), lambda a: 255 - a, True),
+        "threshold": (lambda s, d: ctx.threshold(s, d, 100, 200), lambda a: orc.threshold(a, 100, 200), True),
+        "gray": (lambda s, d: ctx.grayscale(s, d), orc.grayscale, True),
+        "erode": (lambda s, d: ctx.erode(s, d, dip.ops.SQUARE_MASK), lambda a: orc.erode(a, orc.SQUARE_MASK), False),
+        "conv5sep": (lambda s, d: ctx.convolve_separable(s, d, orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1),
+                     lambda a: orc.filter2d_separable(a, orc.BLUR_5X5_1X5, orc.BLUR_5X5_5X1), False),
+        "blur": (lambda s, d: ctx.gaussian_blur3x3(s, d), orc.gaussian_blur3x3, False),
+        "box": (lambda s, d: ctx.convolve(s, d, np.full((3, 3), 0.125, np.float32)),      # the tiled generic kernel
+                lambda a: orc.filter2d(a, np.full((3, 3), 0.125, np.float32)), False),
+    }
+    names = list(ops)
+    rops = {p: op for _, p, op in ctx.reference_ops()}
+    chain = [rops["inversion"], rops["gaussian-blur-3x3"], rops["threshold"]]
+    for trial, steps in enumerate((12, 40, 150)):       # 150 > the tracker's window of 64 nodes
+        n = 7
+        dev = [ctx.image(w, h, c) for _ in range(n)]
+        ctx.apply_chain(chain, dev[0], dev[1])            # the chain's scratch stack must exist before recording
+        ctx.sync()
+        program = []
+        ctx.graph_begin()
+        for step in range(steps):
+            if rng.random() < 0.1:
+                s, d = int(rng.integers(n)), int(rng.integers(n))
+                d = (s + 1) % n if d == s else d
+                ctx.apply_chain(chain, dev[s], dev[d])
+                program.append((lambda a: orc.threshold(orc.gaussian_blur3x3(255 - a), 127, 255), s, d))
+                continue
+            name = names[int(rng.integers(len(names)))]
+            gpu_fn, cpu_fn, inplace_ok = ops[name]
+            s, d = int(rng.integers(n)), int(rng.integers(n))
+            if d == s and not inplace_ok:
+                d = (s + 1) % n
+            gpu_fn(dev[s], dev[d])
+            program.append((cpu_fn, s, d))
+        g = ctx.graph_end()
+        for rep in range(2):
+            host = [rng.integers(0, 256, (h, w, c), dtype=np.uint8) for _ in range(n)]
+            for k in range(n):
+                dev[k].upload(host[k])
+            ctx.sync()
+            g.launch()
+            if rep == 1:
+                g.launch()                                # back to back: the second replay starts from the first one's results
+            for _ in range(rep + 1):
+                for cpu_fn, s, d in program:
+                    host[d] = cpu_fn(host[s])
+            for k in range(n):
+                assert np.array_equal(dev[k].download(), host[k]), (trial, rep, k)
+        g.close()
+        for im in dev:
+            im.close()
+
+
 def test_tensor_core_gaussian_is_bit_exact(ctx, dip, orc, kat):
     """gauss_umma.cu (knob "umma"): the fused 1x5+5x1 Gaussian as two banded-Toeplitz tcgen05.mma.kind::i8 products with
     TMEM accumulators.  Same bits as the SIMD kernel and the oracle: edge shapes, 1/3/4 channels, stacks, row bands, and
