@@ -49,7 +49,7 @@ Knobs g_knobs;
 
 // One warp band of the fused Gaussian -> erosion kernel below.  EDGE: the tile touches the image rim, so Gaussian
 // values outside the image count as 255 (+inf) for the erosion; CLIP: partial last chunk of an unpadded row.
-template <int C, int R, bool EDGE, bool CLIP, bool FULL, bool MAPPED, bool PRE>
+template <int C, int R, bool EDGE, bool CLIP, bool FULL, bool MAPPED, bool PRE, int kUnroll = 5>
 __device__ __forceinline__ void fused_band(const uint8_t* colp, const StencilParams& p, int cx, int yw, int f, int lane) {
     const int n_out = FULL ? R : min(R, p.out_y1 - yw);  // FULL: compile-time trip count (no remainder loop)
     // Gaussian bytes outside [0, rowbytes) count as 255 for the erosion: per-lane masks in packed form
@@ -107,7 +107,7 @@ __device__ __forceinline__ void fused_band(const uint8_t* colp, const StencilPar
     hpass(colp + 5 * kRowBytes, h4);
     gauss_hmin(1, m1);
     h0 = h1; h1 = h2; h2 = h3; h3 = h4;
-#pragma unroll 5
+#pragma unroll kUnroll
     for (int i = 0; i < n_out; ++i) {
         hpass(colp + (i + 6) * kRowBytes, h4);
         Acc8 m2;
@@ -139,7 +139,7 @@ __device__ __forceinline__ void fused_band(const uint8_t* colp, const StencilPar
 // one lane; a warp computes R+2 Gaussian rows for R output rows.  No second shared-memory tile, no
 // __syncthreads after the load.
 // =================================================================================================
-template <int C, int R, int kWarps, bool MAPPED, int kMinCtas = 0>
+template <int C, int R, int kWarps, bool MAPPED, int kMinCtas = 0, int kUnroll = 5>
 __global__ void __launch_bounds__(kWarps * 32, kMinCtas) fused_g5e3_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p) {
     constexpr int kThreads = kWarps * 32;
     constexpr int TO = kWarps * R;        // output rows per tile
@@ -194,12 +194,12 @@ __global__ void __launch_bounds__(kWarps * 32, kMinCtas) fused_g5e3_kernel(const
     } else {
         if (clip) fused_band<C, R, true, true, false, false, false>(colp, p, cx, yw, f, lane);
         else if (border) fused_band<C, R, true, false, false, false, false>(colp, p, cx, yw, f, lane);
-        else if (yw + R <= p.out_y1) fused_band<C, R, false, false, true, false, false>(colp, p, cx, yw, f, lane);
+        else if (yw + R <= p.out_y1) fused_band<C, R, false, false, true, false, false, kUnroll>(colp, p, cx, yw, f, lane);
         else fused_band<C, R, false, false, false, false, false>(colp, p, cx, yw, f, lane);
     }
 }
 
-template <int C, int R, int kWarps, bool MAPPED, int kMinCtas = 0>
+template <int C, int R, int kWarps, bool MAPPED, int kMinCtas = 0, int kUnroll = 5>
 int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps) {
     constexpr int TO = kWarps * R, ROWS = TO + 6;
     constexpr int smem_bytes = ROWS * kRowBytes + 16;
@@ -226,12 +226,12 @@ int launch_fused_g5e3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const 
     static std::atomic<uint64_t> attr_set{0};
     const uint64_t dev_bit = 1ull << (ctx->device & 63);
     if (!(attr_set.load(std::memory_order_relaxed) & dev_bit)) {
-        DIP_CUDA(ctx, cudaFuncSetAttribute(fused_g5e3_kernel<C, R, kWarps, MAPPED, kMinCtas>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
+        DIP_CUDA(ctx, cudaFuncSetAttribute(fused_g5e3_kernel<C, R, kWarps, MAPPED, kMinCtas, kUnroll>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
         attr_set.fetch_or(dev_bit, std::memory_order_relaxed);
     }
     const LaunchMode mode = plan_tiled_launch(ctx, src, dst, g);
     p.wait_prev = mode != kNoWait;
-    DIP_CUDA(ctx, launch_kernel(mode, fused_g5e3_kernel<C, R, kWarps, MAPPED, kMinCtas>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
+    DIP_CUDA(ctx, launch_kernel(mode, fused_g5e3_kernel<C, R, kWarps, MAPPED, kMinCtas, kUnroll>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
                                 dim3(kWarps * 32), smem_bytes, ctx->compute, *map, p));
     DIP_CHECK_LAUNCH(ctx, "fused_g5e3_kernel");
     return DIP_OK;
@@ -559,6 +559,9 @@ int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, co
                 case 5: return launch_fused_g5e3<1, 30, 3, false>(ctx, src, dst, g, nullptr);
                 case 6: return launch_fused_g5e3<1, 15, 4, false, 6>(ctx, src, dst, g, nullptr);
                 case 7: return launch_fused_g5e3<1, 45, 2, false>(ctx, src, dst, g, nullptr);
+                case 8: return launch_fused_g5e3<1, 15, 4, false, 0, 1>(ctx, src, dst, g, nullptr);
+                case 9: return launch_fused_g5e3<1, 15, 4, false, 0, 15>(ctx, src, dst, g, nullptr);
+                case 10: return launch_fused_g5e3<1, 15, 4, false, 0, 3>(ctx, src, dst, g, nullptr);
                 default: break;
             }
             return mapped ? launch_fused_g5e3<1, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<1, 15, 4, false>(ctx, src, dst, g, nullptr);

@@ -8,7 +8,7 @@ dip = load(); L = dip.lib()
 ctx = dip.Context(0)
 fused = dip.make_op("gauss5x5_erode3x3")
 shapes = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4, 5, 6, 7]
-names = {0: "15 rows x 4 warps (shipped)", 1: "30 x 2", 2: "30 x 4", 3: "15 x 4, 5 CTAs/SM by registers", 4: "15 x 2", 5: "30 x 3", 6: "15 x 4, 6 CTAs/SM by registers", 7: "45 x 2"}
+names = {0: "15 rows x 4 warps (shipped)", 1: "30 x 2", 2: "30 x 4", 3: "15 x 4, 5 CTAs/SM by registers", 4: "15 x 2", 5: "30 x 3", 6: "15 x 4, 6 CTAs/SM by registers", 7: "45 x 2", 8: "15 x 4, row loop not unrolled", 9: "15 x 4, row loop unrolled 15x", 10: "15 x 4, row loop unrolled 3x"}
 w, h = 65536, 16384
 src = ctx.image(w, h, 1).synth_fill(seed=1); dst = ctx.image(w, h, 1)
 L.dip_debug_set(b"fused_shape", 0)
