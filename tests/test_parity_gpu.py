@@ -1155,6 +1155,61 @@ def test_recorded_random_programs_replay_like_the_cpu(ctx, dip, orc):
             im.close()
 
 
+def test_one_context_per_thread_concurrently(dip, orc):
+    """include/dip.h: "one dip_ctx per (host thread, GPU)".  Six host threads, each with its own context on the same GPU,
+    run all reference operations, a chain, a pipeline through host buffers, a recorded graph and a JPEG round trip at the
+    same time; everything process-wide in the library (kernel attributes, the reference op table, the staging-copy pool,
+    the nvJPEG binding) is hit concurrently.  Every result must equal the CPU's."""
+    import threading
+    data = open(os.path.join(ROOT, "data", "fundus.jpg"), "rb").read()
+    errors = []
+
+    def worker(t: int):
+        try:
+            rng = np.random.default_rng(900 + t)
+            c = (1, 3, 4)[t % 3]
+            with dip.Context(0) as cx:
+                rops = {p: op for _, p, op in cx.reference_ops()}
+                for rep in range(3):
+                    img = rng.integers(0, 256, (2, 90 + 17 * t, 400 + 33 * t, c), dtype=np.uint8)
+                    src = cx.from_array(img)
+                    dst = cx.image_like(src)
+                    for (prefix, name, args), (_, ofn) in zip(dip.REFERENCE_OPS, orc.OPERATIONS):
+                        getattr(cx, name)(src, dst, *args)
+                        got = dst.download()
+                        for f in range(2):
+                            assert np.array_equal(got[f], ofn(img[f])), (t, rep, prefix)
+                    chain = [rops["inversion"], rops["gaussian-blur-3x3"], rops["threshold"]]
+                    cx.apply_chain(chain, src, dst)
+                    cx.sync()
+                    cx.graph_begin()
+                    cx.apply_chain(chain, src, dst)
+                    g = cx.graph_end()
+                    g.launch()
+                    got = dst.download()
+                    for f in range(2):
+                        assert np.array_equal(got[f], orc.threshold(orc.gaussian_blur3x3(255 - img[f]), 127, 255)), (t, rep, "chain")
+                    g.close()
+                    outs = [np.empty_like(img), np.empty_like(img)]
+                    cx.run_ops_host(img, [rops["inversion"], rops["erosion-square"]], outs, chunk_frames=1)   # pageable host memory: the copy pool
+                    assert np.array_equal(outs[0], 255 - img) and np.array_equal(outs[1][1], orc.erode(img[1], orc.SQUARE_MASK)), (t, rep, "pipeline")
+                    src.close(); dst.close()
+                if t % 2 == 0:
+                    one = cx.imdecode(data)
+                    bits = cx.imencode(one, quality=90)
+                    assert bits[:2] == b"\xff\xd8"
+                    one.close()
+        except Exception as e:  # noqa: BLE001
+            errors.append((t, repr(e)))
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(6)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    assert not errors, errors
+
+
 def test_tensor_core_gaussian_is_bit_exact(ctx, dip, orc, kat):
     """gauss_umma.cu (knob "umma"): the fused 1x5+5x1 Gaussian as two banded-Toeplitz tcgen05.mma.kind::i8 products with
     TMEM accumulators.  Same bits as the SIMD kernel and the oracle: edge shapes, 1/3/4 channels, stacks, row bands, and
