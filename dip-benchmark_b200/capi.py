@@ -37,7 +37,7 @@ class DeviceInfo(C.Structure):
 class Op(C.Structure):
     _fields_ = [("kind", C.c_int), ("thresh", C.c_uint8), ("maxval", C.c_uint8), ("mask", C.c_void_p),
                 ("mask_w", C.c_int), ("mask_h", C.c_int), ("kernel", C.c_void_p), ("kw", C.c_int), ("kh", C.c_int),
-                ("kernel_col", C.c_void_p)]
+                ("kernel_col", C.c_void_p), ("thresh16", C.c_uint16), ("maxval16", C.c_uint16)]
 
 
 class IpcHandle(C.Structure):
@@ -95,6 +95,9 @@ def lib() -> C.CDLL:
         "dip_image_rows": ([vp, vp, i, i, P(vp)], i),
         "dip_image_destroy": ([vp], i),
         "dip_image_get_info": ([vp, P(ImageInfo)], i),
+        "dip_image_create16": ([vp, i, i, i, i, P(vp)], i),
+        "dip_image_depth": ([vp, P(i)], i),
+        "dip_threshold16": ([vp, vp, vp, C.c_uint16, C.c_uint16], i),
         "dip_host_alloc": ([P(vp), sz], i),
         "dip_host_free": ([vp], i),
         "dip_host_register": ([vp, sz], i),

@@ -47,6 +47,7 @@ int check_pair(dip_ctx* ctx, const dip_image* src, const dip_image* dst, bool al
     if (a.width != b.width || a.height != b.height || a.channels != b.channels || a.frames != b.frames)
         return fail(ctx, DIP_ERR_SHAPE, "src %dx%dx%d(x%d) and dst %dx%dx%d(x%d) differ", a.width,
                     a.height, a.channels, a.frames, b.width, b.height, b.channels, b.frames);
+    if (a.bps != b.bps) return fail(ctx, DIP_ERR_SHAPE, "src has %d-bit samples, dst %d-bit", 8 * a.bps, 8 * b.bps);
     if (!allow_inplace && a.base == b.base)
         return fail(ctx, DIP_ERR_SHAPE, "stencil operations cannot run in place (src == dst)");
     return DIP_OK;
@@ -395,18 +396,19 @@ int dip_get_device_info(dip_ctx* ctx, dip_device_info* info) {
 }
 
 // ---- images -----------------------------------------------------------------------------
-int dip_image_create_batch(dip_ctx* ctx, int w, int h, int c, int frames, dip_image** out) {
+static int create_stack(dip_ctx* ctx, int w, int h, int c, int frames, int bps, dip_image** out) {
     if (!ctx || !out) return fail(ctx, DIP_ERR_ARG, "null argument");
     *out = nullptr;
     if (w < 1 || h < 1 || frames < 1) return fail(ctx, DIP_ERR_ARG, "bad geometry %dx%d x%d frames", w, h, frames);
     if (c != 1 && c != 3 && c != 4) return fail(ctx, DIP_ERR_ARG, "channels must be 1, 3 or 4 (got %d)", c);
-    if ((long long)w * c > (1ll << 30)) return fail(ctx, DIP_ERR_ARG, "row too long");
+    if ((long long)w * c * bps > (1ll << 30)) return fail(ctx, DIP_ERR_ARG, "row too long");
     dip_image* im = nullptr;
     int rc = new_image(ctx, &im);
     if (rc != DIP_OK) return rc;
     ImgView& v = im->v;
     v.width = w; v.height = h; v.channels = c; v.frames = frames;
-    v.rowbytes = w * c;
+    v.bps = bps;
+    v.rowbytes = w * c * bps;
     v.pitch = round_up((size_t)v.rowbytes, 16);
     v.frame_stride = v.pitch * (size_t)h;
     v.pad_writable = true;
@@ -421,6 +423,16 @@ int dip_image_create_batch(dip_ctx* ctx, int w, int h, int c, int frames, dip_im
     im->owned = true;
     v.base = static_cast<uint8_t*>(im->alloc);
     *out = im;
+    return DIP_OK;
+}
+
+int dip_image_create_batch(dip_ctx* ctx, int w, int h, int c, int frames, dip_image** out) { return create_stack(ctx, w, h, c, frames, 1, out); }
+
+int dip_image_create16(dip_ctx* ctx, int w, int h, int c, int frames, dip_image** out) { return create_stack(ctx, w, h, c, frames, 2, out); }
+
+int dip_image_depth(const dip_image* im, int* bits) {
+    if (!im || !bits) return fail(nullptr, DIP_ERR_ARG, "null argument");
+    *bits = 8 * im->v.bps;
     return DIP_OK;
 }
 
@@ -442,7 +454,7 @@ int dip_image_wrap(dip_ctx* ctx, void* p, int w, int h, int c, int frames, size_
     dip_image* im = nullptr;
     int rc = new_image(ctx, &im);
     if (rc != DIP_OK) return rc;
-    im->v = ImgView{static_cast<uint8_t*>(p), pitch, frame_stride, w, h, c, frames, w * c, false};
+    im->v = ImgView{static_cast<uint8_t*>(p), pitch, frame_stride, w, h, c, frames, w * c, 1, false};
     *out = im;
     return DIP_OK;
 }

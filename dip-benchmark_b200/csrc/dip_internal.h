@@ -24,7 +24,8 @@ struct ImgView {
     size_t pitch;         // bytes between rows (multiple of 16)
     size_t frame_stride;  // bytes between frames (multiple of 16)
     int width, height, channels, frames;
-    int rowbytes;         // width * channels
+    int rowbytes;         // width * channels * bps
+    int bps;              // bytes per sample: 1 (u8) or 2 (u16, little endian like the host's arrays)
     // The bytes between the end of a row and the next 16-byte boundary are padding the kernels may overwrite (library-owned
     // allocations).  False for dip_image_wrap: there they can be the caller's pixels (a region of interest of a wider image).
     bool pad_writable;
@@ -296,6 +297,14 @@ int check_pair(dip_ctx* ctx, const dip_image* src, const dip_image* dst, bool al
 int enqueue_upload(dip_ctx* ctx, const ImgView& v, const uint8_t* host, size_t host_pitch);
 int enqueue_download(dip_ctx* ctx, const ImgView& v, uint8_t* host, size_t host_pitch, bool* completed);
 
+// ---- 16-bit images (depth16.cu): the point operations that are not byte-wise, and the direct stencil kernel --------
+int launch_threshold16(dip_ctx* ctx, const ImgView& src, const ImgView& dst, uint16_t thresh, uint16_t maxval);
+int launch_grayscale16(dip_ctx* ctx, const ImgView& src, const ImgView& dst);
+// mode 0 erode, 1 dilate, 2 correlation rounded half to even (filter2D), 3 correlation rounded half up (GaussianBlur);
+// taps as (dx, dy, weight) triples in pixels
+int launch_direct16(dip_ctx* ctx, int mode, const dip_image* src, dip_image* dst, int valid_y0, int valid_y1, int out_y0, int out_y1,
+                    int dst_y0, const int8_t* dx, const int8_t* dy, const float* wt, int ntaps);
+
 // ---- kernels' host launchers (point_ops.cu) -----------------------------------------
 enum PointOp { kCopy = 0, kInvert = 1, kThreshold = 2 };
 int launch_point(dip_ctx* ctx, PointOp op, const ImgView& src, const ImgView& dst, uint8_t thresh,
@@ -349,6 +358,8 @@ struct SmallTaps {
     int kh;
 };
 int launch_generic_tiled(dip_ctx* ctx, int mode, int kw, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps);
+// does the tile's 16-byte halo reach a kw x kh mask / kernel on this image (8-bit: up to 7 x 7; 16-bit: 5 x 5, 7 x 7 for one channel)?
+bool generic_tiled_reach(const dip_image* src, int kw, int kh);
 
 // TMA descriptor of an image view seen as a (pitch/4 words, rows, frames) u32 tensor.
 int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out, bool swizzle128 = false);

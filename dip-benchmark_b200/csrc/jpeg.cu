@@ -190,6 +190,7 @@ int check_target(dip_ctx* ctx, const dip_image* img, int first, int count, const
     if (!img) return fail(ctx, DIP_ERR_ARG, "%s: null image", what);
     if (img->device != ctx->device) return fail(ctx, DIP_ERR_ARG, "%s: the image lives on another device", what);
     if (img->v.channels != 3 && img->v.channels != 1) return fail(ctx, DIP_ERR_UNSUPPORTED, "%s: 1- or 3-channel images only", what);
+    if (img->v.bps != 1) return fail(ctx, DIP_ERR_UNSUPPORTED, "%s: 8-bit images only", what);
     if (first < 0 || count < 0 || first + count > img->v.frames) return fail(ctx, DIP_ERR_ARG, "%s: frames [%d, %d) outside the stack of %d", what, first, first + count, img->v.frames);
     return DIP_OK;
 }

@@ -102,7 +102,9 @@ int dip_apply(dip_ctx* ctx, const dip_op* op, const dip_image* src, dip_image* d
         case DIP_OP_COPY: return dip_copy(ctx, src, dst);
         case DIP_OP_INVERT: return dip_invert(ctx, src, dst);
         case DIP_OP_GRAYSCALE: return dip_grayscale(ctx, src, dst);
-        case DIP_OP_THRESHOLD: return dip_threshold(ctx, src, dst, op->thresh, op->maxval);
+        case DIP_OP_THRESHOLD:
+            if (src && src->v.bps == 2 && (op->thresh16 || op->maxval16)) return dip_threshold16(ctx, src, dst, op->thresh16, op->maxval16);
+            return dip_threshold(ctx, src, dst, op->thresh, op->maxval);
         case DIP_OP_ERODE: return dip_erode(ctx, src, dst, op->mask, op->mask_w, op->mask_h);
         case DIP_OP_DILATE: return dip_dilate(ctx, src, dst, op->mask, op->mask_w, op->mask_h);
         case DIP_OP_ERODE_SEPARABLE: return dip_erode_separable(ctx, src, dst, op->mask_w, op->mask_h);
@@ -212,7 +214,7 @@ int ensure_scratch(dip_ctx* ctx, const dip_image* like, dip_image** out) { retur
 
 int dip::scratch_view(dip_ctx* ctx, int slot, const dip_image* like, dip_image** out) {
     dip_image* s = ctx->scratch[slot];
-    if (!(s && s->v.width == like->v.width && s->v.height == like->v.height && s->v.channels == like->v.channels && s->v.frames >= like->v.frames)) {
+    if (!(s && s->v.width == like->v.width && s->v.height == like->v.height && s->v.channels == like->v.channels && s->v.bps == like->v.bps && s->v.frames >= like->v.frames)) {
         if (ctx->capturing) return fail(ctx, DIP_ERR_UNSUPPORTED, "run this chain once before recording it: its scratch stack is allocated on first use");
         if (s) {
             dep_touch(ctx);
@@ -220,7 +222,8 @@ int dip::scratch_view(dip_ctx* ctx, int slot, const dip_image* like, dip_image**
             dip_image_destroy(s);
             ctx->scratch[slot] = nullptr;
         }
-        int rc = dip_image_create_batch(ctx, like->v.width, like->v.height, like->v.channels, like->v.frames, &ctx->scratch[slot]);
+        int rc = like->v.bps == 2 ? dip_image_create16(ctx, like->v.width, like->v.height, like->v.channels, like->v.frames, &ctx->scratch[slot])
+                                  : dip_image_create_batch(ctx, like->v.width, like->v.height, like->v.channels, like->v.frames, &ctx->scratch[slot]);
         if (rc != DIP_OK) return rc;
     }
     return dip_image_view(ctx, ctx->scratch[slot], 0, like->v.frames, out);
@@ -277,6 +280,20 @@ int dip_apply_chain(dip_ctx* ctx, const dip_op* ops, int n, const dip_image* src
     if (!ctx || !ops || n < 1) return fail(ctx, DIP_ERR_ARG, "bad argument");
     int rc = check_pair(ctx, src, dst, true);
     if (rc != DIP_OK) return rc;
+    if (src->v.bps == 2) {
+        // 16-bit samples: the operations one after the other (the per-byte maps a chain folds are 8-bit maps), with the
+        // same ping-pong between the scratch stack and dst
+        dip_image* scratch16 = nullptr;
+        if (n > 1 && (rc = ensure_scratch(ctx, src, &scratch16)) != DIP_OK) return rc;
+        const dip_image* in = src;
+        for (int j = 1; j <= n && rc == DIP_OK; ++j) {
+            dip_image* out = ((n - j) & 1) ? scratch16 : dst;
+            rc = dip_apply(ctx, &ops[j - 1], in, out);
+            in = out;
+        }
+        dip_image_destroy(scratch16);
+        return rc;
+    }
     std::vector<ChainPass> plan;
     if ((rc = plan_chain(ctx, ops, n, src->v.channels, plan)) != DIP_OK) return rc;
     const int k = (int)plan.size();
@@ -356,6 +373,7 @@ int apply_rows_impl(dip_ctx* ctx, const dip_op* op, const dip_image* src, int va
                     dip_image* dst, int dst_row0, const dip_peer_rows* above, const dip_peer_rows* below) {
     if (!ctx || !op || !src || !dst) return fail(ctx, DIP_ERR_ARG, "null argument");
     if (out_rows < 1 || valid_rows < 1) return fail(ctx, DIP_ERR_ARG, "empty row range");
+    if (src->v.bps != dst->v.bps) return fail(ctx, DIP_ERR_SHAPE, "src has %d-bit samples, dst %d-bit", 8 * src->v.bps, 8 * dst->v.bps);
     RowGeom g{valid_row0, valid_row0 + valid_rows, out_row0, out_row0 + out_rows, dst_row0};
     int rc = set_peer(ctx, src, above, &g.peer_top, &g.peer_top_y0, &g.peer_top_y1);
     if (rc == DIP_OK) rc = set_peer(ctx, src, below, &g.peer_bot, &g.peer_bot_y0, &g.peer_bot_y1);

@@ -414,13 +414,23 @@ int dip_threshold(dip_ctx* ctx, const dip_image* src, dip_image* dst, uint8_t th
     int rc = check_pair(ctx, src, dst, true);
     if (rc != DIP_OK) return rc;
     if ((rc = begin_op(ctx, src, dst)) != DIP_OK) return rc;
+    if (src->v.bps == 2) return launch_threshold16(ctx, src->v, dst->v, thresh, maxval);   // the same numbers on 16-bit samples, like cv.threshold
     return launch_point(ctx, kThreshold, src->v, dst->v, thresh, maxval);
+}
+
+int dip_threshold16(dip_ctx* ctx, const dip_image* src, dip_image* dst, uint16_t thresh, uint16_t maxval) {
+    int rc = check_pair(ctx, src, dst, true);
+    if (rc != DIP_OK) return rc;
+    if (src->v.bps != 2) return fail(ctx, DIP_ERR_ARG, "dip_threshold16 needs 16-bit images (dip_image_create16)");
+    if ((rc = begin_op(ctx, src, dst)) != DIP_OK) return rc;
+    return launch_threshold16(ctx, src->v, dst->v, thresh, maxval);
 }
 
 int dip_grayscale(dip_ctx* ctx, const dip_image* src, dip_image* dst) {
     int rc = check_pair(ctx, src, dst, true);
     if (rc != DIP_OK) return rc;
     if ((rc = begin_op(ctx, src, dst)) != DIP_OK) return rc;
+    if (src->v.bps == 2) return launch_grayscale16(ctx, src->v, dst->v);
     return launch_grayscale(ctx, src->v, dst->v);
 }
 

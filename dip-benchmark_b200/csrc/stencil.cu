@@ -467,10 +467,12 @@ int stencil_morph(dip_ctx* ctx, Morph m, const dip_image* src, dip_image* dst, c
     for (int i = 0; i < mw * mh; ++i) nz += mask[i] != 0;
     if (nz == 0) return fail(ctx, DIP_ERR_ARG, "mask has no non-zero tap");
     const bool dil = m == Morph::Dilate;
-    const int top = classify_morph(m, mask, mw, mh);
+    const bool wide = src->v.bps == 2;   // 16-bit samples: the benchmark's dedicated kernels are 8-bit only
+    if (wide && (g.peer_top || g.peer_bot)) return fail(ctx, DIP_ERR_UNSUPPORTED, "16-bit images cannot read peer rows");
+    const int top = wide ? -1 : classify_morph(m, mask, mw, mh);
     if (top >= 0) return launch_tiled_op(ctx, top, src, dst, g, maps);
     if (maps) return fail(ctx, DIP_ERR_UNSUPPORTED, "per-byte maps fuse into the tiled kernels only");
-    if (mw <= 7 && mh <= 7 && !g_knobs.direct_generic && tma_ok(src)) {  // small masks: the tiled generic kernel
+    if (generic_tiled_reach(src, mw, mh) && !g_knobs.direct_generic && tma_ok(src)) {  // small masks: the tiled generic kernel
         SmallTaps t{};
         t.kh = mh;
         for (int j = 0; j < mh; ++j)
@@ -487,6 +489,7 @@ int stencil_morph(dip_ctx* ctx, Morph m, const dip_image* src, dip_image* dst, c
                 p.wt[p.ntaps] = 1.0f;
                 ++p.ntaps;
             }
+    if (wide) return launch_direct16(ctx, dil ? 1 : 0, src, dst, g.valid_y0, g.valid_y1, g.out_y0, g.out_y1, g.dst_y0, p.dx, p.dy, p.wt, p.ntaps);
     return dil ? launch_generic<1>(ctx, p) : launch_generic<0>(ctx, p);
 }
 
@@ -496,10 +499,12 @@ int stencil_convolve(dip_ctx* ctx, const dip_image* src, dip_image* dst, const f
     if (kw * kh > kMaxTaps || kw > 127 || kh > 127) return fail(ctx, DIP_ERR_UNSUPPORTED, "kernel larger than %d taps", kMaxTaps);
     int rc = check_geom(ctx, src, dst, g);
     if (rc != DIP_OK) return rc;
-    const int top = classify_convolve(k, kw, kh);
+    const bool wide = src->v.bps == 2;
+    if (wide && (g.peer_top || g.peer_bot)) return fail(ctx, DIP_ERR_UNSUPPORTED, "16-bit images cannot read peer rows");
+    const int top = wide ? -1 : classify_convolve(k, kw, kh);
     if (top >= 0) return launch_tiled_op(ctx, top, src, dst, g, maps);
     if (maps) return fail(ctx, DIP_ERR_UNSUPPORTED, "per-byte maps fuse into the tiled kernels only");
-    if (kw <= 7 && kh <= 7 && !g_knobs.direct_generic && tma_ok(src)) {  // small kernels: the tiled generic kernel
+    if (generic_tiled_reach(src, kw, kh) && !g_knobs.direct_generic && tma_ok(src)) {  // small kernels: the tiled generic kernel
         SmallTaps t{};
         t.kh = kh;
         for (int j = 0; j < kh; ++j)
@@ -516,6 +521,8 @@ int stencil_convolve(dip_ctx* ctx, const dip_image* src, dip_image* dst, const f
                 p.wt[p.ntaps] = k[j * kw + i];
                 ++p.ntaps;
             }
+    if (p.ntaps == 0) { p.dx[0] = 0; p.dy[0] = 0; p.wt[0] = 0.0f; p.ntaps = 1; }   // an all-zero kernel: zeros out
+    if (wide) return launch_direct16(ctx, 2, src, dst, g.valid_y0, g.valid_y1, g.out_y0, g.out_y1, g.dst_y0, p.dx, p.dy, p.wt, p.ntaps);
     return launch_generic<2>(ctx, p);
 }
 
@@ -524,7 +531,7 @@ int stencil_convolve_sep(dip_ctx* ctx, const dip_image* src, dip_image* dst, con
     if (!krow || !kcol || kw < 1 || kh < 1) return fail(ctx, DIP_ERR_ARG, "bad kernel");
     int rc = check_geom(ctx, src, dst, g);
     if (rc != DIP_OK) return rc;
-    const int top = classify_convolve_sep(krow, kw, kcol, kh);
+    const int top = src->v.bps == 2 ? -1 : classify_convolve_sep(krow, kw, kcol, kh);
     if (top >= 0) return launch_tiled_op(ctx, top, src, dst, g, maps);
     // Any other pair of kernels: the reference's two calls through `aux` (opencv:84-90, sycl:347-356) -- a 1 x kw pass
     // whose result is rounded and saturated to u8 exactly as `aux` is, then a kh x 1 pass -- with the ctx's scratch stack
@@ -548,6 +555,24 @@ int stencil_convolve_sep(dip_ctx* ctx, const dip_image* src, dip_image* dst, con
 int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps) {
     int rc = check_geom(ctx, src, dst, g);
     if (rc != DIP_OK) return rc;
+    if (src->v.bps == 2) {   // 16-bit samples: the two operations one after the other through the ctx's `aux` stack
+        if (maps || g.peer_top || g.peer_bot) return fail(ctx, DIP_ERR_UNSUPPORTED, "16-bit images: no fused maps, no peer rows");
+        static const float b5[5] = {1 / 16.f, 4 / 16.f, 6 / 16.f, 4 / 16.f, 1 / 16.f};
+        float k5[25];
+        for (int j = 0; j < 5; ++j)
+            for (int i = 0; i < 5; ++i) k5[5 * j + i] = b5[j] * b5[i];
+        static const uint8_t ones[9] = {1, 1, 1, 1, 1, 1, 1, 1, 1};
+        dip_image* aux = nullptr;
+        if ((rc = scratch_view(ctx, 1, src, &aux)) != DIP_OK) return rc;
+        RowGeom g1 = g;
+        g1.out_y0 = std::max(g.valid_y0, g.out_y0 - 1);
+        g1.out_y1 = std::min(g.valid_y1, g.out_y1 + 1);
+        g1.dst_y0 = g1.out_y0;
+        rc = stencil_convolve(ctx, src, aux, k5, 5, 5, g1, nullptr);
+        if (rc == DIP_OK) rc = stencil_morph(ctx, Morph::Erode, aux, dst, ones, 3, 3, g, nullptr);
+        dip_image_destroy(aux);
+        return rc;
+    }
     const bool mapped = maps && !(maps->pre.identity() && maps->post.identity());
     switch (src->v.channels) {
         case 1:
@@ -574,6 +599,23 @@ int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, co
 int stencil_gaussian3(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const ChainMaps* maps) {
     int rc = check_geom(ctx, src, dst, g);
     if (rc != DIP_OK) return rc;
+    if (src->v.bps == 2) {   // 16-bit samples: ([1 2 1] x [1 2 1] sum + 8) >> 4, exact in fp32 (20 bits), rounded half up
+        if (maps) return fail(ctx, DIP_ERR_UNSUPPORTED, "per-byte maps fuse into the tiled kernels only");
+        if (g.peer_top || g.peer_bot) return fail(ctx, DIP_ERR_UNSUPPORTED, "16-bit images cannot read peer rows");
+        static const float b3[3] = {0.25f, 0.5f, 0.25f};
+        if (!g_knobs.direct_generic && tma_ok(src)) {
+            SmallTaps t{};
+            t.kh = 3;
+            for (int j = 0; j < 3; ++j)
+                for (int i = 0; i < 3; ++i) t.w[j][i] = b3[j] * b3[i];
+            return launch_generic_tiled(ctx, 3, 3, src, dst, g, t);
+        }
+        int8_t dx[9], dy[9];
+        float wt[9];
+        for (int j = 0; j < 3; ++j)
+            for (int i = 0; i < 3; ++i) { dx[3 * j + i] = (int8_t)(i - 1); dy[3 * j + i] = (int8_t)(j - 1); wt[3 * j + i] = b3[j] * b3[i]; }
+        return launch_direct16(ctx, 3, src, dst, g.valid_y0, g.valid_y1, g.out_y0, g.out_y1, g.dst_y0, dx, dy, wt, 9);
+    }
     return launch_tiled_op(ctx, kGauss3, src, dst, g, maps);
 }
 

@@ -9,6 +9,8 @@
 // (2*RX+1) x 16 FFMAs (convolution: fp32 accumulation in row-major tap order, cvRound, saturate -- bit-exact for
 // dyadic kernels, within 1 LSB otherwise, like the direct kernel in stencil.cu) or FMNMXs (erosion / dilation; the
 // bytes are exact in fp32).  Larger masks keep the direct kernel.
+// BPS = 2 instantiates the same kernel for 16-bit samples (depth16.cu): a thread's 16 bytes are 8 samples, the pixel
+// stride in the tile is C * 2 bytes, results saturate at 65535, and mode 3 rounds half up (GaussianBlur).
 #include "stencil_tiled.cuh"
 
 namespace dip {
@@ -74,22 +76,34 @@ __device__ __forceinline__ float win_byte(const uint32_t (&w)[12]) {
     return __uint_as_float(__byte_perm(w[B / 4], 0x4B000000u, 0x7650 + (B & 3))) - 8388608.0f;
 }
 
-template <int MODE, int C, int RX, int N, int I = 0>
+// 16-bit sample starting at byte `B` (even) of the window as fp32
+template <int B>
+__device__ __forceinline__ float win_half(const uint32_t (&w)[12]) {
+    static_assert(B >= 0 && B < 48 && (B & 1) == 0, "window");
+    return __uint_as_float(__byte_perm(w[B / 4], 0x4B000000u, (B & 2) ? 0x7632 : 0x7610)) - 8388608.0f;
+}
+
+template <int MODE, int C, int RX, int BPS, int N, int I = 0>
 struct RowTaps {
-    // acc[b] (op)= wt[k] * f[b + k*C] for every tap column k and own byte b; f[q] = window byte 16 - RX*C + q
+    // acc[b] (op)= wt[k] * f[b + k*C] for every tap column k and own sample b; f[q] = the sample at window byte
+    // 16 - RX*C*BPS + q*BPS
     static __device__ __forceinline__ void fill(const uint32_t (&w)[12], float (&f)[N]) {
         if constexpr (I < N) {
-            f[I] = win_byte<16 - RX * C + I>(w);
-            RowTaps<MODE, C, RX, N, I + 1>::fill(w, f);
+            if constexpr (BPS == 1) f[I] = win_byte<16 - RX * C + I>(w);
+            else f[I] = win_half<16 - RX * C * 2 + 2 * I>(w);
+            RowTaps<MODE, C, RX, BPS, N, I + 1>::fill(w, f);
         }
     }
 };
 
-template <int MODE, int C, int RX>  // MODE 0 erode, 1 dilate, 2 correlation
+template <int MODE, int C, int RX, int BPS = 1>  // MODE 0 erode, 1 dilate, 2 correlation (RNE), 3 correlation (round half up)
 __global__ void __launch_bounds__(kGenWarps * 32) generic_tiled_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p, const SmallTaps taps) {
     constexpr int kThreads = kGenWarps * 32;
-    constexpr int N = 16 + 2 * RX * C;   // bytes of a tap row one thread reads
-    static_assert(RX * C <= 16, "horizontal reach beyond the 16-byte halo");
+    constexpr int CB = C * BPS;              // bytes per pixel
+    constexpr int NOUT = 16 / BPS;           // samples a thread produces per row
+    constexpr int N = NOUT + 2 * RX * C;     // samples of a tap row one thread reads
+    constexpr float kTop = BPS == 1 ? 255.0f : 65535.0f;
+    static_assert(RX * CB <= 16, "horizontal reach beyond the 16-byte halo");
     extern __shared__ __align__(128) uint8_t smem[];
     const int ry = taps.kh / 2;
     const int rows = kGenTH + 2 * ry;
@@ -110,10 +124,10 @@ __global__ void __launch_bounds__(kGenWarps * 32) generic_tiled_kernel(const __g
     if (threadIdx.x == 0) tma_load_3d(tile, &tmap, bar, (bx0 - kHalo) / 4, ytop, f);
     __syncthreads();
     mbar_wait(bar, 0);
-    const bool border = bx0 == 0 || bx0 + kTileBytes + RX * C > p.rowbytes || ytop < p.valid_y0 || ytop + rows > p.valid_y1;
+    const bool border = bx0 == 0 || bx0 + kTileBytes + RX * CB > p.rowbytes || ytop < p.valid_y0 || ytop + rows > p.valid_y1;
     if (border) {
         __syncthreads();
-        patch_borders_rt<C, kThreads>(tile, p, bx0, ytop, RX, ry, rows, MODE != 2, MODE == 1 ? 0 : 255);
+        patch_borders_rt<CB, kThreads>(tile, p, bx0, ytop, RX, ry, rows, MODE < 2, MODE == 1 ? 0 : 255);   // per byte: 0xFFFF for 16-bit erosion
     }
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -126,9 +140,9 @@ __global__ void __launch_bounds__(kGenWarps * 32) generic_tiled_kernel(const __g
     const int valid = p.dst_exact ? min(16, p.rowbytes - cx) : 16;
 
     for (int i = 0; i < nrows; ++i) {
-        float acc[16];
+        float acc[NOUT];
 #pragma unroll
-        for (int b = 0; b < 16; ++b) acc[b] = MODE == 0 ? 255.0f : 0.0f;
+        for (int b = 0; b < NOUT; ++b) acc[b] = MODE == 0 ? kTop : 0.0f;
         for (int dy = 0; dy < taps.kh; ++dy) {
             const uint8_t* rp = colp + (i + dy) * kRowBytes;
             const uint4 wa = *reinterpret_cast<const uint4*>(rp - 16);
@@ -136,27 +150,30 @@ __global__ void __launch_bounds__(kGenWarps * 32) generic_tiled_kernel(const __g
             const uint4 wc = *reinterpret_cast<const uint4*>(rp + 16);
             const uint32_t w[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
             float fw[N];
-            RowTaps<MODE, C, RX, N>::fill(w, fw);
+            RowTaps<MODE, C, RX, BPS, N>::fill(w, fw);
 #pragma unroll
             for (int k = 0; k <= 2 * RX; ++k) {
                 const float wt = taps.w[dy][k];
-                if (MODE == 2) {
+                if (MODE >= 2) {
 #pragma unroll
-                    for (int b = 0; b < 16; ++b) acc[b] = __fmaf_rn(wt, fw[b + k * C], acc[b]);
+                    for (int b = 0; b < NOUT; ++b) acc[b] = __fmaf_rn(wt, fw[b + k * C], acc[b]);
                 } else if (wt != 0.0f) {   // uniform: is this position of the mask set?
 #pragma unroll
-                    for (int b = 0; b < 16; ++b) acc[b] = MODE == 0 ? fminf(acc[b], fw[b + k * C]) : fmaxf(acc[b], fw[b + k * C]);
+                    for (int b = 0; b < NOUT; ++b) acc[b] = MODE == 0 ? fminf(acc[b], fw[b + k * C]) : fmaxf(acc[b], fw[b + k * C]);
                 }
             }
         }
         uint32_t o[4];
+        constexpr int kPerWord = 4 / BPS;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             uint32_t word = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                const int r = MODE == 2 ? min(max(__float2int_rn(acc[4 * j + b]), 0), 255) : (int)acc[4 * j + b];  // cvRound + saturate_cast<uchar>
-                word |= (uint32_t)r << (8 * b);
+            for (int b = 0; b < kPerWord; ++b) {
+                const float a = acc[kPerWord * j + b];
+                // cvRound (or round half up) + saturate_cast
+                const int r = MODE == 2 ? min(max(__float2int_rn(a), 0), (int)kTop) : MODE == 3 ? min(max(__float2int_rd(a + 0.5f), 0), (int)kTop) : (int)a;
+                word |= (uint32_t)r << (8 * BPS * b);
             }
             o[j] = word;
         }
@@ -164,7 +181,7 @@ __global__ void __launch_bounds__(kGenWarps * 32) generic_tiled_kernel(const __g
     }
 }
 
-template <int MODE, int C, int RX>
+template <int MODE, int C, int RX, int BPS = 1>
 int launch_generic_tiled_t(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
     const int rows = kGenTH + 2 * (taps.kh / 2);
     const int smem_bytes = rows * kRowBytes + 16;
@@ -184,7 +201,7 @@ int launch_generic_tiled_t(dip_ctx* ctx, const dip_image* src, dip_image* dst, c
     if (p.tiles_y > 65535 || src->v.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
     const LaunchMode mode = plan_tiled_launch(ctx, src, dst, g);
     p.wait_prev = mode != kNoWait;
-    DIP_CUDA(ctx, launch_kernel(mode, generic_tiled_kernel<MODE, C, RX>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
+    DIP_CUDA(ctx, launch_kernel(mode, generic_tiled_kernel<MODE, C, RX, BPS>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
                                 dim3(kGenWarps * 32), smem_bytes, ctx->compute, *map, p, taps));
     DIP_CHECK_LAUNCH(ctx, "generic_tiled_kernel");
     return DIP_OK;
@@ -200,6 +217,24 @@ int launch_generic_tiled_c(dip_ctx* ctx, int rx, const dip_image* src, dip_image
     return fail(ctx, DIP_ERR_ARG, "bad horizontal radius %d", rx);
 }
 
+// 16-bit samples: the 16-byte halo reaches 2 pixels of 3 or 4 channels, 3 pixels of one channel (generic_tiled_reach)
+template <int MODE>
+int launch_generic_tiled_16(dip_ctx* ctx, int rx, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
+    const int c = src->v.channels;
+    if (rx == 1) {
+        if (c == 1) return launch_generic_tiled_t<MODE, 1, 1, 2>(ctx, src, dst, g, taps);
+        if (c == 3) return launch_generic_tiled_t<MODE, 3, 1, 2>(ctx, src, dst, g, taps);
+        if (c == 4) return launch_generic_tiled_t<MODE, 4, 1, 2>(ctx, src, dst, g, taps);
+    } else if (rx == 2) {
+        if (c == 1) return launch_generic_tiled_t<MODE, 1, 2, 2>(ctx, src, dst, g, taps);
+        if (c == 3) return launch_generic_tiled_t<MODE, 3, 2, 2>(ctx, src, dst, g, taps);
+        if (c == 4) return launch_generic_tiled_t<MODE, 4, 2, 2>(ctx, src, dst, g, taps);
+    } else if (rx == 3 && c == 1) {
+        return launch_generic_tiled_t<MODE, 1, 3, 2>(ctx, src, dst, g, taps);
+    }
+    return fail(ctx, DIP_ERR_ARG, "bad horizontal radius %d for %d 16-bit channels", rx, c);
+}
+
 template <int MODE>
 int launch_generic_tiled_m(dip_ctx* ctx, int rx, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
     switch (src->v.channels) {
@@ -212,8 +247,22 @@ int launch_generic_tiled_m(dip_ctx* ctx, int rx, const dip_image* src, dip_image
 
 }  // namespace
 
+bool generic_tiled_reach(const dip_image* src, int kw, int kh) {
+    if (kw > 7 || kh > 7) return false;
+    return std::max(1, kw / 2) * src->v.channels * src->v.bps <= 16;
+}
+
 int launch_generic_tiled(dip_ctx* ctx, int mode, int kw, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
     const int rx = std::max(1, kw / 2);
+    if (src->v.bps == 2) {
+        switch (mode) {
+            case 0: return launch_generic_tiled_16<0>(ctx, rx, src, dst, g, taps);
+            case 1: return launch_generic_tiled_16<1>(ctx, rx, src, dst, g, taps);
+            case 2: return launch_generic_tiled_16<2>(ctx, rx, src, dst, g, taps);
+            case 3: return launch_generic_tiled_16<3>(ctx, rx, src, dst, g, taps);
+        }
+        return fail(ctx, DIP_ERR_ARG, "bad mode");
+    }
     switch (mode) {
         case 0: return launch_generic_tiled_m<0>(ctx, rx, src, dst, g, taps);
         case 1: return launch_generic_tiled_m<1>(ctx, rx, src, dst, g, taps);

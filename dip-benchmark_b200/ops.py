@@ -39,6 +39,9 @@ class Image:
         check(lib().dip_image_get_info(self._h, C.byref(info)), ctx._h)
         self.width, self.height, self.channels, self.frames = info.width, info.height, info.channels, info.frames
         self.pitch, self.frame_stride, self.device_ptr = info.pitch, info.frame_stride, info.device_ptr
+        bits = C.c_int()
+        check(lib().dip_image_depth(self._h, C.byref(bits)), ctx._h)
+        self.dtype = np.dtype(np.uint16 if bits.value == 16 else np.uint8)   # 16-bit stacks: dip_image_create16
 
     @property
     def shape(self):
@@ -47,7 +50,7 @@ class Image:
 
     @property
     def nbytes(self) -> int:
-        return self.frames * self.height * self.width * self.channels
+        return self.frames * self.height * self.width * self.channels * self.dtype.itemsize
 
     def close(self):
         if self._h:
@@ -62,8 +65,8 @@ class Image:
 
     # -- transfers (opencv/benchmark.py:92-93) --------------------------------------------
     def upload(self, array: np.ndarray) -> "Image":
-        a = np.ascontiguousarray(array, dtype=np.uint8)
-        if a.size != self.nbytes:
+        a = np.ascontiguousarray(array, dtype=self.dtype)
+        if a.nbytes != self.nbytes:
             raise ValueError(f"array of {a.shape} does not match image stack {self.shape}")
         self._keep = a  # borrowed until the next sync
         check(lib().dip_upload(self.ctx._h, self._h, a.ctypes.data, 0), self.ctx._h)
@@ -71,8 +74,8 @@ class Image:
 
     def download(self, out: np.ndarray | None = None, sync: bool = True) -> np.ndarray:
         if out is None:
-            out = np.empty(self.shape, dtype=np.uint8)
-        if out.size != self.nbytes or not out.flags.c_contiguous:
+            out = np.empty(self.shape, dtype=self.dtype)
+        if out.nbytes != self.nbytes or not out.flags.c_contiguous:
             raise ValueError("bad output array")
         check(lib().dip_download(self.ctx._h, self._h, out.ctypes.data, 0), self.ctx._h)
         if sync:
@@ -220,18 +223,27 @@ class Context:
     def jpeg_backend(self) -> str:
         return lib().dip_jpeg_backend(self._h).decode()
 
+    def image16(self, width: int, height: int, channels: int = 3, frames: int = 1) -> Image:
+        """A stack of 16-bit unsigned images (dip_image_create16)."""
+        h = C.c_void_p()
+        check(lib().dip_image_create16(self._h, width, height, channels, frames, C.byref(h)), self._h)
+        return Image(self, h.value)
+
     def image_like(self, other: Image) -> Image:
+        if other.dtype == np.uint16:
+            return self.image16(other.width, other.height, other.channels, other.frames)
         return self.image(other.width, other.height, other.channels, other.frames)
 
     def from_array(self, array: np.ndarray) -> Image:
         """cv.UMat(cpu_image) -- opencv/benchmark.py:42 (array: HxWxC, HxW, or NxHxWxC)."""
-        a = np.asarray(array, dtype=np.uint8)
+        a = np.asarray(array)
+        a = a if a.dtype == np.uint16 else a.astype(np.uint8, copy=False)   # uint16 arrays become 16-bit stacks
         if a.ndim == 2:
             a = a[:, :, None]
         if a.ndim == 3:
             a = a[None]
         n, hgt, w, c = a.shape
-        img = self.image(w, hgt, c, n)
+        img = self.image16(w, hgt, c, n) if a.dtype == np.uint16 else self.image(w, hgt, c, n)
         img.upload(a)
         self.sync()
         return img
@@ -248,6 +260,10 @@ class Context:
 
     def threshold(self, src: Image, dst: Image, thresh: int = 127, maxval: int = 255):
         check(lib().dip_threshold(self._h, src._h, dst._h, thresh, maxval), self._h)
+
+    def threshold16(self, src: Image, dst: Image, thresh: int, maxval: int):
+        """cv.threshold on 16-bit images with 16-bit arguments (dip_threshold16)."""
+        check(lib().dip_threshold16(self._h, src._h, dst._h, thresh, maxval), self._h)
 
     def erode(self, src: Image, dst: Image, mask: np.ndarray):
         m = np.ascontiguousarray(mask, dtype=np.uint8)

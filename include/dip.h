@@ -24,9 +24,13 @@
  *    SYCL backend waits after every call, sycl:335; dip_sync() gives that).
  *  - one dip_ctx per (host thread, GPU); a ctx is not thread-safe.
  *  - there is no CPU fallback: without a CUDA device dip_init fails.
- *  - pixel type: 8-bit unsigned only, like every backend of the reference (cv.imread's CV_8U, sycl uint8_t*).
- *    16-bit images (last item) are NOT implemented: there is no entry point that takes them, and
- *    wrapping 16-bit memory as twice as many 8-bit columns gives the 8-bit result of those bytes, not a 16-bit one.
+ *  - pixel type: 8-bit unsigned, like every backend of the reference (cv.imread's CV_8U, sycl uint8_t*).  16-bit
+ *    unsigned images (last item) are a second sample type: dip_image_create16 makes a stack of
+ *    them (little-endian u16 samples, as a numpy / cv::Mat CV_16U array holds them) and every operation below accepts it
+ *    with the semantics OpenCV gives CV_16U (the same formulas on the wider type; src and dst must have the same
+ *    depth).  They are not benchmark kernels: stencils run on the generic tiled / direct kernels, op chains apply
+ *    their operations one by one, and the host pipelines, JPEG, peer rows and dip_image_wrap are 8-bit only
+ *    (DIP_ERR_UNSUPPORTED / DIP_ERR_SHAPE).
  *  - masks / kernels: the benchmark's seven run on dedicated kernels; any other mask / kernel of up to 7 x 7 taps on a
  *    tiled generic kernel, up to 15 x 15 (225 taps) on a direct one; larger ones return DIP_ERR_UNSUPPORTED.
  */
@@ -98,6 +102,9 @@ DIP_API int dip_image_view(dip_ctx* ctx, dip_image* parent, int first, int count
 DIP_API int dip_image_rows(dip_ctx* ctx, dip_image* parent, int row0, int rows, dip_image** view);
 DIP_API int dip_image_destroy(dip_image* img);
 DIP_API int dip_image_get_info(const dip_image* img, dip_image_info* info);
+/* a stack of `frames` images of 16-bit unsigned samples (pitch = W*C*2 rounded up to 16); dip_image_depth: 8 or 16 */
+DIP_API int dip_image_create16(dip_ctx* ctx, int width, int height, int channels, int frames, dip_image** img);
+DIP_API int dip_image_depth(const dip_image* img, int* bits_per_sample);
 
 /* ---- pinned host buffers for the transfer path -------------------------------- */
 DIP_API int dip_host_alloc(void** ptr, size_t bytes);
@@ -155,6 +162,9 @@ DIP_API int dip_grayscale(dip_ctx* ctx, const dip_image* src, dip_image* dst);
  * dst = src > thresh ? maxval : 0 on every byte */
 DIP_API int dip_threshold(dip_ctx* ctx, const dip_image* src, dip_image* dst, uint8_t thresh,
                           uint8_t maxval);
+/* the same on 16-bit images with 16-bit arguments (dip_threshold on a 16-bit image compares with its 8-bit numbers) */
+DIP_API int dip_threshold16(dip_ctx* ctx, const dip_image* src, dip_image* dst, uint16_t thresh,
+                            uint16_t maxval);
 
 /* ---- stencil operations ---------------------------------------------------------- */
 /* "Erosion": cv.erode(image, mask) opencv:98-99 (and the 1x3 / 3x1 calls :77-78),
@@ -218,6 +228,7 @@ typedef struct dip_op {
     const float* kernel;   /* convolve, or the row kernel of CONVOLVE_SEPARABLE */
     int kw, kh;
     const float* kernel_col; /* column kernel of CONVOLVE_SEPARABLE */
+    uint16_t thresh16, maxval16; /* THRESHOLD on 16-bit images; both 0: use thresh / maxval */
 } dip_op;
 
 /* dst = op(src) for one entry of an operation list */

@@ -153,3 +153,29 @@ def test_pattern_cases_match_reference_outputs(orc):
         img = g[f"{name}/input"]
         for prefix, fn in orc.OPERATIONS:
             assert np.array_equal(fn(img), g[f"{name}/{prefix}"]), f"{name} {prefix}"
+
+
+_U16_EXTRA = {
+    "threshold16": lambda o16, a: o16.threshold(a, 30000, 65535),
+    "dilate-5x3": lambda o16, a: o16.dilate(a, np.array([[1, 0, 1, 1, 0], [0, 1, 1, 0, 1], [1, 1, 0, 0, 1]], np.uint8)),
+    "erode-7x7": lambda o16, a: o16.erode(a, (np.arange(49).reshape(7, 7) % 3 != 0).astype(np.uint8)),
+    "erode-9x9": lambda o16, a: o16.erode(a, np.ones((9, 9), np.uint8)),
+    "sharpen-saturating": lambda o16, a: o16.filter2d(a, np.array([[0, -1, 0], [-1, 5, -1], [0, -1, 0]], np.float32)),
+    "conv-9x1-dyadic": lambda o16, a: o16.filter2d(a, (np.array([1, 2, 4, 8, 2, 8, 4, 2, 1], np.float32) / 32).reshape(9, 1)),
+}
+
+
+def test_16bit_restatement_matches_reference_outputs():
+    """oracle/oracle16.py (numpy) against the reference's cv2 calls on CV_16U input (tests/golden/u16_cases.npz, written by
+    make_golden_u16.py with cv2 4.13): 7 shapes x {1,3,4} channels x 18 operations, 0 mismatching samples."""
+    from oracle import oracle16 as o16
+    g = np.load(os.path.join(ROOT, "tests", "golden", "u16_cases.npz"))
+    cases = sorted({k.split("/")[0] for k in g.files})
+    assert len(cases) == 21
+    fns = {name: (lambda a, f=fn: f(a)) for name, fn in o16.OPERATIONS}
+    fns.update({name: (lambda a, f=fn: f(o16, a)) for name, fn in _U16_EXTRA.items()})
+    for key in cases:
+        img = g[f"{key}/input"]
+        assert img.dtype == np.uint16
+        for name, fn in fns.items():
+            assert np.array_equal(fn(img), g[f"{key}/{name}"]), (key, name)

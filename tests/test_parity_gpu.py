@@ -1155,6 +1155,74 @@ def test_recorded_random_programs_replay_like_the_cpu(ctx, dip, orc):
             im.close()
 
 
+def test_16bit_images_match_reference_outputs_and_oracle(ctx, dip, orc):
+    """16-bit unsigned images (dip_image_create16): every operation with the semantics the reference's cv2
+    calls give CV_16U input -- golden vectors written by cv2 (tests/golden/u16_cases.npz), plus the numpy restatement
+    (oracle/oracle16.py) on stacks, larger shapes, row bands, a chain, and the direct kernels behind the knob."""
+    from oracle import oracle16 as o16
+    from test_oracle import _U16_EXTRA
+    g = np.load(os.path.join(ROOT, "tests", "golden", "u16_cases.npz"))
+    m53 = np.array([[1, 0, 1, 1, 0], [0, 1, 1, 0, 1], [1, 1, 0, 0, 1]], np.uint8)
+    m77 = (np.arange(49).reshape(7, 7) % 3 != 0).astype(np.uint8)
+    calls = {prefix: (name, args) for prefix, name, args in dip.REFERENCE_OPS}
+    calls.update({"threshold16": ("threshold16", (30000, 65535)), "dilate-5x3": ("dilate", (m53,)), "erode-7x7": ("erode", (m77,)),
+                  "erode-9x9": ("erode", (np.ones((9, 9), np.uint8),)),
+                  "sharpen-saturating": ("convolve", (np.array([[0, -1, 0], [-1, 5, -1], [0, -1, 0]], np.float32),)),
+                  "conv-9x1-dyadic": ("convolve", ((np.array([1, 2, 4, 8, 2, 8, 4, 2, 1], np.float32) / 32).reshape(9, 1),))})
+    L = dip.lib()
+    for knob in (0, 1):                                # 1: everything through the direct kernels
+        L.dip_debug_set(b"direct_generic", knob)
+        try:
+            for key in sorted({k.split("/")[0] for k in g.files}):
+                img = g[f"{key}/input"]
+                src = ctx.from_array(img)
+                assert src.dtype == np.uint16
+                dst = ctx.image_like(src)
+                for prefix, (name, args) in calls.items():
+                    getattr(ctx, name)(src, dst, *args)
+                    got = dst.download().reshape(img.shape)
+                    assert np.array_equal(got, g[f"{key}/{prefix}"]), (knob, key, prefix, int((got != g[f"{key}/{prefix}"]).sum()))
+                src.close(); dst.close()
+        finally:
+            L.dip_debug_set(b"direct_generic", 0)
+    # stacks and larger shapes against the numpy restatement
+    rng = np.random.default_rng(1616)
+    for c in (1, 3, 4):
+        stack = rng.integers(0, 65536, (3, 150, 700, c), dtype=np.uint16)
+        stack[:, :40, :90] = (stack[:, :40, :90] // 16384) * 21845
+        src = ctx.from_array(stack)
+        dst = ctx.image_like(src)
+        for (prefix, name, args), (_, ofn) in zip(dip.REFERENCE_OPS, o16.OPERATIONS):
+            getattr(ctx, name)(src, dst, *args)
+            got = dst.download()
+            for f in range(3):
+                assert np.array_equal(got[f], ofn(stack[f])), (c, prefix, f)
+        # the Gaussian -> erosion pair and a chain (applied one by one for 16-bit samples)
+        ctx.gauss5x5_erode3x3(src, dst)
+        assert np.array_equal(dst.download()[1], o16.erode(o16.filter2d(stack[1], orc.BLUR_5X5), orc.SQUARE_MASK)), c
+        rops = {p: op for _, p, op in ctx.reference_ops()}
+        ctx.apply_chain([rops["inversion"], rops["gaussian-blur-3x3"], rops["erosion-cross"]], src, dst)
+        assert np.array_equal(dst.download()[2], o16.erode(o16.gaussian_blur3x3(o16.invert(stack[2])), orc.CROSS_MASK)), c
+        # row bands with explicit valid rows (interior band edges read real rows, true edges reflect)
+        op = rops["convolution-gaussian-blur-5x5"]
+        for (r0, r1) in ((0, 50), (50, 97), (97, 150)):
+            ctx.apply_rows(op, src, 0, 150, r0, r1 - r0, dst, r0)
+        assert np.array_equal(dst.download()[0], o16.filter2d(stack[0], orc.BLUR_5X5)), c
+        # transfers, checksum
+        assert np.array_equal(src.download(), stack)
+        src.close(); dst.close()
+    # depth mismatches and the 8-bit-only paths say so
+    a16, a8 = ctx.image16(64, 64, 3), ctx.image(64, 64, 3)
+    with pytest.raises(dip.DipError) as e:
+        ctx.invert(a16, a8)
+    assert e.value.code == -2   # DIP_ERR_SHAPE
+    with pytest.raises(dip.DipError):
+        ctx.imencode(a16)
+    with pytest.raises(dip.DipError):
+        ctx.threshold16(a8, a8, 1, 2)
+    a16.close(); a8.close()
+
+
 def test_one_context_per_thread_concurrently(dip, orc):
     """include/dip.h: "one dip_ctx per (host thread, GPU)".  Six host threads, each with its own context on the same GPU,
     run all reference operations, a chain, a pipeline through host buffers, a recorded graph and a JPEG round trip at the
