@@ -360,6 +360,7 @@ struct SmallTaps {
 int launch_generic_tiled(dip_ctx* ctx, int mode, int kw, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps);
 // does the tile's 16-byte halo reach a kw x kh mask / kernel on this image (8-bit: up to 7 x 7; 16-bit: 5 x 5, 7 x 7 for one channel)?
 bool generic_tiled_reach(const dip_image* src, int kw, int kh);
+extern bool g_generic_float_morph;   // development knob "float_morph"
 
 // TMA descriptor of an image view seen as a (pitch/4 words, rows, frames) u32 tensor.
 int get_tmap(dip_ctx* ctx, dip_image* img, int box_words, int box_rows, const CUtensorMap** out, bool swizzle128 = false);

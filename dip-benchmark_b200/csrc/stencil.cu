@@ -632,6 +632,7 @@ int dip_debug_set(const char* key, int value) {
     else if (!strcmp(key, "direct_generic")) g_knobs.direct_generic = value;
     else if (!strcmp(key, "umma")) g_knobs.umma = value;
     else if (!strcmp(key, "fused_shape")) g_knobs.fused_shape = value;
+    else if (!strcmp(key, "float_morph")) g_generic_float_morph = value != 0;
     else if (!strcmp(key, "no_pad")) g_no_occupancy_pad = value != 0;
     else return fail(nullptr, DIP_ERR_ARG, "unknown knob %s", key);
     return DIP_OK;

@@ -139,12 +139,18 @@ __global__ void __launch_bounds__(kGenWarps * 32) generic_tiled_kernel(const __g
     uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
     const int valid = p.dst_exact ? min(16, p.rowbytes - cx) : 16;
 
-    for (int i = 0; i < nrows; ++i) {
-        float acc[NOUT];
+    // kM output rows per pass share their source rows (kM + kh - 1 conversions to fp32 for kM results instead of kM * kh);
+    // every result still accumulates its taps in row-major order, so the fp32 sums are what one row at a time gives
+    constexpr int kM = 32 / NOUT;   // 2 rows of 16 bytes, 4 rows of 8 16-bit samples: 32 accumulators
+    static_assert(kGenRows % kM == 0, "rows per warp");
+    for (int i = 0; i < nrows; i += kM) {
+        float acc[kM][NOUT];
 #pragma unroll
-        for (int b = 0; b < NOUT; ++b) acc[b] = MODE == 0 ? kTop : 0.0f;
-        for (int dy = 0; dy < taps.kh; ++dy) {
-            const uint8_t* rp = colp + (i + dy) * kRowBytes;
+        for (int m = 0; m < kM; ++m)
+#pragma unroll
+            for (int b = 0; b < NOUT; ++b) acc[m][b] = MODE == 0 ? kTop : 0.0f;
+        for (int t = 0; t < taps.kh + kM - 1; ++t) {   // tile row i + t; rows past the band's end exist in the tile and feed no stored result
+            const uint8_t* rp = colp + (i + t) * kRowBytes;
             const uint4 wa = *reinterpret_cast<const uint4*>(rp - 16);
             const uint4 wb = *reinterpret_cast<const uint4*>(rp);
             const uint4 wc = *reinterpret_cast<const uint4*>(rp + 16);
@@ -152,32 +158,126 @@ __global__ void __launch_bounds__(kGenWarps * 32) generic_tiled_kernel(const __g
             float fw[N];
             RowTaps<MODE, C, RX, BPS, N>::fill(w, fw);
 #pragma unroll
-            for (int k = 0; k <= 2 * RX; ++k) {
-                const float wt = taps.w[dy][k];
-                if (MODE >= 2) {
+            for (int m = 0; m < kM; ++m) {
+                const int dy = t - m;
+                if (dy < 0 || dy >= taps.kh) continue;   // uniform over the launch
 #pragma unroll
-                    for (int b = 0; b < NOUT; ++b) acc[b] = __fmaf_rn(wt, fw[b + k * C], acc[b]);
-                } else if (wt != 0.0f) {   // uniform: is this position of the mask set?
+                for (int k = 0; k <= 2 * RX; ++k) {
+                    const float wt = taps.w[dy][k];
+                    if (MODE >= 2) {
 #pragma unroll
-                    for (int b = 0; b < NOUT; ++b) acc[b] = MODE == 0 ? fminf(acc[b], fw[b + k * C]) : fmaxf(acc[b], fw[b + k * C]);
+                        for (int b = 0; b < NOUT; ++b) acc[m][b] = __fmaf_rn(wt, fw[b + k * C], acc[m][b]);
+                    } else if (wt != 0.0f) {   // uniform: is this position of the mask set?
+#pragma unroll
+                        for (int b = 0; b < NOUT; ++b) acc[m][b] = MODE == 0 ? fminf(acc[m][b], fw[b + k * C]) : fmaxf(acc[m][b], fw[b + k * C]);
+                    }
                 }
             }
         }
-        uint32_t o[4];
         constexpr int kPerWord = 4 / BPS;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t word = 0;
+        for (int m = 0; m < kM; ++m) {
+            if (i + m >= nrows) break;
+            uint32_t o[4];
 #pragma unroll
-            for (int b = 0; b < kPerWord; ++b) {
-                const float a = acc[kPerWord * j + b];
-                // cvRound (or round half up) + saturate_cast
-                const int r = MODE == 2 ? min(max(__float2int_rn(a), 0), (int)kTop) : MODE == 3 ? min(max(__float2int_rd(a + 0.5f), 0), (int)kTop) : (int)a;
-                word |= (uint32_t)r << (8 * BPS * b);
+            for (int j = 0; j < 4; ++j) {
+                uint32_t word = 0;
+#pragma unroll
+                for (int b = 0; b < kPerWord; ++b) {
+                    const float a = acc[m][kPerWord * j + b];
+                    // cvRound (or round half up) + saturate_cast
+                    const int r = MODE == 2 ? min(max(__float2int_rn(a), 0), (int)kTop) : MODE == 3 ? min(max(__float2int_rd(a + 0.5f), 0), (int)kTop) : (int)a;
+                    word |= (uint32_t)r << (8 * BPS * b);
+                }
+                o[j] = word;
             }
-            o[j] = word;
+            store16(dptr + (size_t)(i + m) * p.dst.pitch, make_uint4(o[0], o[1], o[2], o[3]), valid);
         }
-        store16(dptr + (size_t)i * p.dst.pitch, make_uint4(o[0], o[1], o[2], o[3]), valid);
+    }
+}
+
+// ---- arbitrary masks in packed integer arithmetic (8-bit samples) ---------------------------------------------------
+// Erosion / dilation need no arithmetic but minima, so an arbitrary mask can run on the packed u16x2 lanes of the
+// dedicated kernels instead of fp32: a row is unpacked once per (output row, mask row) into even / odd byte streams
+// (load_row), the tap at column k is the compile-time selection pair_at<4j + k*C> of neighbouring packed words, and only
+// WHETHER it takes part is a run-time (launch-uniform) test of the mask.  ~150 instructions per 16 output bytes for a full
+// 3x3 mask against ~330 in fp32.  Reach of the 8-word window: RX * C <= 8 bytes.
+template <int C, int K, bool MAX>
+__device__ __forceinline__ void morph_tap(const Row8& r, Acc8& a) {
+#define DIP_MT(j)                                                                                          \
+    a.v[2 * j] = MAX ? __vmaxu2(a.v[2 * j], pair_at<4 * j + K * C>(r)) : __vminu2(a.v[2 * j], pair_at<4 * j + K * C>(r));          \
+    a.v[2 * j + 1] = MAX ? __vmaxu2(a.v[2 * j + 1], pair_at<4 * j + 1 + K * C>(r)) : __vminu2(a.v[2 * j + 1], pair_at<4 * j + 1 + K * C>(r));
+    DIP_MT(0) DIP_MT(1) DIP_MT(2) DIP_MT(3)
+#undef DIP_MT
+}
+template <int C, int RX, bool MAX, int K = -RX>
+__device__ __forceinline__ void morph_row(const Row8& r, Acc8& a, const float* wrow) {
+    if constexpr (K <= RX) {
+        if (wrow[K + RX] != 0.0f) morph_tap<C, K, MAX>(r, a);   // uniform over the launch
+        morph_row<C, RX, MAX, K + 1>(r, a, wrow);
+    }
+}
+
+template <int C, int RX, bool MAX>
+__global__ void __launch_bounds__(kGenWarps * 32) generic_morph_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p, const SmallTaps taps) {
+    constexpr int kThreads = kGenWarps * 32;
+    static_assert(RX * C <= 8, "tap outside the 8-word window");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int ry = taps.kh / 2;
+    const int rows = kGenTH + 2 * ry;
+    uint8_t* tile = smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + rows * kRowBytes);
+    const int tx = blockIdx.x, ty = blockIdx.y, f = blockIdx.z;
+    const int bx0 = tx * kTileBytes;
+    const int y0 = p.out_y0 + ty * kGenTH;
+    const int ytop = y0 - ry;
+
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar, rows * kRowBytes);
+    }
+    pdl_wait(p.wait_prev);
+    if (threadIdx.x == 0) tma_load_3d(tile, &tmap, bar, (bx0 - kHalo) / 4, ytop, f);
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const bool border = bx0 == 0 || bx0 + kTileBytes + RX * C > p.rowbytes || ytop < p.valid_y0 || ytop + rows > p.valid_y1;
+    if (border) {
+        __syncthreads();
+        patch_borders_rt<C, kThreads>(tile, p, bx0, ytop, RX, ry, rows, true, MAX ? 0 : 255);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cx = bx0 + 16 * lane;
+    const int yw = y0 + warp * kGenRows;
+    if (cx >= ((p.rowbytes + 15) & ~15) || yw >= p.out_y1) return;
+    const int nrows = min(kGenRows, p.out_y1 - yw);
+    const uint8_t* colp = tile + (warp * kGenRows) * kRowBytes + kHalo + 16 * lane;
+    uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
+    const int valid = p.dst_exact ? min(16, p.rowbytes - cx) : 16;
+    // kM output rows per pass share their source rows: kM + kh - 1 rows are unpacked for kM results instead of kM * kh
+    constexpr int kM = 4;
+    static_assert(kGenRows % kM == 0, "rows per warp");
+    for (int i = 0; i < nrows; i += kM) {
+        Acc8 a[kM];
+#pragma unroll
+        for (int m = 0; m < kM; ++m)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) a[m].v[k] = MAX ? 0u : 0x00FF00FFu;
+        for (int t = 0; t < taps.kh + kM - 1; ++t) {   // tile row i + t; rows past the band's end exist in the tile and feed no stored result
+            Row8 row;
+            load_row(colp + (i + t) * kRowBytes, row);
+#pragma unroll
+            for (int m = 0; m < kM; ++m) {
+                const int dy = t - m;
+                if (dy >= 0 && dy < taps.kh) morph_row<C, RX, MAX>(row, a[m], taps.w[dy]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kM; ++m)
+            if (i + m < nrows)
+                store16(dptr + (size_t)(i + m) * p.dst.pitch,
+                        make_uint4(pack_lo(a[m].v[0], a[m].v[1]), pack_lo(a[m].v[2], a[m].v[3]), pack_lo(a[m].v[4], a[m].v[5]), pack_lo(a[m].v[6], a[m].v[7])), valid);
     }
 }
 
@@ -205,6 +305,46 @@ int launch_generic_tiled_t(dip_ctx* ctx, const dip_image* src, dip_image* dst, c
                                 dim3(kGenWarps * 32), smem_bytes, ctx->compute, *map, p, taps));
     DIP_CHECK_LAUNCH(ctx, "generic_tiled_kernel");
     return DIP_OK;
+}
+
+template <int C, int RX, bool MAX>
+int launch_generic_morph_t(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
+    const int rows = kGenTH + 2 * (taps.kh / 2);
+    const int smem_bytes = rows * kRowBytes + 16;
+    const CUtensorMap* map = nullptr;
+    int rc = get_tmap(ctx, const_cast<dip_image*>(src), kBoxWords, rows, &map);
+    if (rc != DIP_OK) return rc;
+    StencilParams p{};
+    p.dst = dst->v;
+    p.rowbytes = src->v.rowbytes;
+    p.width = src->v.width;
+    p.valid_y0 = g.valid_y0; p.valid_y1 = g.valid_y1;
+    p.out_y0 = g.out_y0; p.out_y1 = g.out_y1; p.dst_y0 = g.dst_y0;
+    p.tiles_x = (src->v.rowbytes + kTileBytes - 1) / kTileBytes;
+    p.tiles_y = (g.out_y1 - g.out_y0 + kGenTH - 1) / kGenTH;
+    p.dst_exact = exact_rows(dst->v);
+    if (p.tiles_x <= 0 || p.tiles_y <= 0) return DIP_OK;
+    if (p.tiles_y > 65535 || src->v.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
+    const LaunchMode mode = plan_tiled_launch(ctx, src, dst, g);
+    p.wait_prev = mode != kNoWait;
+    DIP_CUDA(ctx, launch_kernel(mode, generic_morph_kernel<C, RX, MAX>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
+                                dim3(kGenWarps * 32), smem_bytes, ctx->compute, *map, p, taps));
+    DIP_CHECK_LAUNCH(ctx, "generic_morph_kernel");
+    return DIP_OK;
+}
+
+// the packed-integer form where the 8-word window reaches (RX * C <= 8), else -1: the caller takes the fp32 kernel
+template <bool MAX>
+int launch_generic_morph(dip_ctx* ctx, int rx, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
+    const int c = src->v.channels;
+    if (c == 1 && rx == 1) return launch_generic_morph_t<1, 1, MAX>(ctx, src, dst, g, taps);
+    if (c == 1 && rx == 2) return launch_generic_morph_t<1, 2, MAX>(ctx, src, dst, g, taps);
+    if (c == 1 && rx == 3) return launch_generic_morph_t<1, 3, MAX>(ctx, src, dst, g, taps);
+    if (c == 3 && rx == 1) return launch_generic_morph_t<3, 1, MAX>(ctx, src, dst, g, taps);
+    if (c == 3 && rx == 2) return launch_generic_morph_t<3, 2, MAX>(ctx, src, dst, g, taps);
+    if (c == 4 && rx == 1) return launch_generic_morph_t<4, 1, MAX>(ctx, src, dst, g, taps);
+    if (c == 4 && rx == 2) return launch_generic_morph_t<4, 2, MAX>(ctx, src, dst, g, taps);
+    return -1;
 }
 
 template <int MODE, int C>
@@ -247,6 +387,8 @@ int launch_generic_tiled_m(dip_ctx* ctx, int rx, const dip_image* src, dip_image
 
 }  // namespace
 
+bool g_generic_float_morph = false;   // development knob "float_morph": arbitrary masks on the fp32 kernel (A/B)
+
 bool generic_tiled_reach(const dip_image* src, int kw, int kh) {
     if (kw > 7 || kh > 7) return false;
     return std::max(1, kw / 2) * src->v.channels * src->v.bps <= 16;
@@ -262,6 +404,10 @@ int launch_generic_tiled(dip_ctx* ctx, int mode, int kw, const dip_image* src, d
             case 3: return launch_generic_tiled_16<3>(ctx, rx, src, dst, g, taps);
         }
         return fail(ctx, DIP_ERR_ARG, "bad mode");
+    }
+    if (mode < 2 && !g_generic_float_morph) {   // erosion / dilation of 8-bit samples: packed minima where the window reaches
+        const int rc = mode == 0 ? launch_generic_morph<false>(ctx, rx, src, dst, g, taps) : launch_generic_morph<true>(ctx, rx, src, dst, g, taps);
+        if (rc != -1) return rc;
     }
     switch (mode) {
         case 0: return launch_generic_tiled_m<0>(ctx, rx, src, dst, g, taps);

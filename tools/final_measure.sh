@@ -5,6 +5,8 @@ o=gpurun_out
 timeout 300 python bench.py > $o/${tag}_bench_n1.json 2> $o/${tag}_bench_n1.err; echo "bench rc=$?"
 timeout 600 python bench.py --impl reference --steps 2 --warmup 1 > $o/${tag}_bench_ref.json 2> $o/${tag}_bench_ref.err; echo "ref rc=$?"
 timeout 300 python bench.py --per-op > $o/${tag}_per_op.md 2> $o/${tag}_per_op.err; echo "per-op rc=$?"
+timeout 200 python tools/depth16_bench.py 16 > $o/${tag}_depth16.md 2>&1; echo "depth16 rc=$?"
+timeout 300 python tools/jpeg_bench.py 32 5 > $o/${tag}_jpeg_bench.md 2>&1; echo "jpeg rc=$?"
 B="python bench.py --no-e2e --no-cpu --no-mosaic --no-single --steps 1 --warmup 3 --min-timed-s 0 --batch 64"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $o/${tag}_launches.csv $B > $o/${tag}_ncu1.log 2>&1; echo "ncu launches rc=$?"
 timeout 600 ncu --set full --clock-control none -k regex:"stencil_kernel|point_flat_kernel|gray3" --launch-skip 60 --launch-count 12 -f -o $o/${tag}_prof $B > $o/${tag}_ncu2.log 2>&1; echo "ncu full rc=$?"
