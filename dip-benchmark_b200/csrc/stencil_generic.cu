@@ -307,7 +307,94 @@ int launch_generic_tiled_t(dip_ctx* ctx, const dip_image* src, dip_image* dst, c
     return DIP_OK;
 }
 
+// The same for 16-bit samples: two neighbouring samples ARE a packed u16x2 word, so there is nothing to unpack -- a tap at
+// q samples is a word of the row (q even) or one funnel of two (q odd).  The thread's 16 bytes are 8 samples = 4 words;
+// the 12-word window (3 x 16 bytes) reaches 8 samples either side: RX * C <= 8.
+template <int Q>   // the word holding samples (Q, Q + 1) relative to the thread's first own sample (word 4 of the window)
+__device__ __forceinline__ uint32_t pair16_at(const uint32_t (&w)[12]) {
+    static_assert(Q >= -8 && Q + 1 < 16, "tap outside the 12-word window");
+    constexpr int q = Q + 8;
+    if constexpr ((q & 1) == 0) return w[q / 2];
+    else return __byte_perm(w[(q - 1) / 2], w[(q + 1) / 2], 0x5432);
+}
+template <int C, int K, bool MAX>
+__device__ __forceinline__ void morph16_tap(const uint32_t (&w)[12], uint32_t (&a)[4]) {
+#define DIP_MT16(j) a[j] = MAX ? __vmaxu2(a[j], pair16_at<2 * j + K * C>(w)) : __vminu2(a[j], pair16_at<2 * j + K * C>(w));
+    DIP_MT16(0) DIP_MT16(1) DIP_MT16(2) DIP_MT16(3)
+#undef DIP_MT16
+}
+template <int C, int RX, bool MAX, int K = -RX>
+__device__ __forceinline__ void morph16_row(const uint32_t (&w)[12], uint32_t (&a)[4], const float* wrow) {
+    if constexpr (K <= RX) {
+        if (wrow[K + RX] != 0.0f) morph16_tap<C, K, MAX>(w, a);   // uniform over the launch
+        morph16_row<C, RX, MAX, K + 1>(w, a, wrow);
+    }
+}
+
 template <int C, int RX, bool MAX>
+__global__ void __launch_bounds__(kGenWarps * 32) generic_morph16_kernel(const __grid_constant__ CUtensorMap tmap, const StencilParams p, const SmallTaps taps) {
+    constexpr int kThreads = kGenWarps * 32;
+    constexpr int CB = 2 * C;
+    static_assert(RX * C <= 8, "tap outside the 12-word window");
+    extern __shared__ __align__(128) uint8_t smem[];
+    const int ry = taps.kh / 2;
+    const int rows = kGenTH + 2 * ry;
+    uint8_t* tile = smem;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(smem + rows * kRowBytes);
+    const int tx = blockIdx.x, ty = blockIdx.y, f = blockIdx.z;
+    const int bx0 = tx * kTileBytes;
+    const int y0 = p.out_y0 + ty * kGenTH;
+    const int ytop = y0 - ry;
+
+    pdl_launch_dependents();
+    if (threadIdx.x == 0) {
+        mbar_init(bar, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar, rows * kRowBytes);
+    }
+    pdl_wait(p.wait_prev);
+    if (threadIdx.x == 0) tma_load_3d(tile, &tmap, bar, (bx0 - kHalo) / 4, ytop, f);
+    __syncthreads();
+    mbar_wait(bar, 0);
+    const bool border = bx0 == 0 || bx0 + kTileBytes + RX * CB > p.rowbytes || ytop < p.valid_y0 || ytop + rows > p.valid_y1;
+    if (border) {
+        __syncthreads();
+        patch_borders_rt<CB, kThreads>(tile, p, bx0, ytop, RX, ry, rows, true, MAX ? 0 : 255);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cx = bx0 + 16 * lane;
+    const int yw = y0 + warp * kGenRows;
+    if (cx >= ((p.rowbytes + 15) & ~15) || yw >= p.out_y1) return;
+    const int nrows = min(kGenRows, p.out_y1 - yw);
+    const uint8_t* colp = tile + (warp * kGenRows) * kRowBytes + kHalo + 16 * lane;
+    uint8_t* dptr = p.dst.base + (size_t)f * p.dst.frame_stride + (size_t)(p.dst_y0 + (yw - p.out_y0)) * p.dst.pitch + cx;
+    const int valid = p.dst_exact ? min(16, p.rowbytes - cx) : 16;
+    constexpr int kM = 4;
+    for (int i = 0; i < nrows; i += kM) {
+        uint32_t a[kM][4];
+#pragma unroll
+        for (int m = 0; m < kM; ++m)
+#pragma unroll
+            for (int k = 0; k < 4; ++k) a[m][k] = MAX ? 0u : 0xFFFFFFFFu;
+        for (int t = 0; t < taps.kh + kM - 1; ++t) {
+            const uint8_t* rp = colp + (i + t) * kRowBytes;
+            const uint4 wa = *reinterpret_cast<const uint4*>(rp - 16);
+            const uint4 wb = *reinterpret_cast<const uint4*>(rp);
+            const uint4 wc = *reinterpret_cast<const uint4*>(rp + 16);
+            const uint32_t w[12] = {wa.x, wa.y, wa.z, wa.w, wb.x, wb.y, wb.z, wb.w, wc.x, wc.y, wc.z, wc.w};
+#pragma unroll
+            for (int m = 0; m < kM; ++m) {
+                const int dy = t - m;
+                if (dy >= 0 && dy < taps.kh) morph16_row<C, RX, MAX>(w, a[m], taps.w[dy]);
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kM; ++m)
+            if (i + m < nrows) store16(dptr + (size_t)(i + m) * p.dst.pitch, make_uint4(a[m][0], a[m][1], a[m][2], a[m][3]), valid);
+    }
+}
+
+template <int C, int RX, bool MAX, int BPS = 1>
 int launch_generic_morph_t(dip_ctx* ctx, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
     const int rows = kGenTH + 2 * (taps.kh / 2);
     const int smem_bytes = rows * kRowBytes + 16;
@@ -327,8 +414,12 @@ int launch_generic_morph_t(dip_ctx* ctx, const dip_image* src, dip_image* dst, c
     if (p.tiles_y > 65535 || src->v.frames > 65535) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
     const LaunchMode mode = plan_tiled_launch(ctx, src, dst, g);
     p.wait_prev = mode != kNoWait;
-    DIP_CUDA(ctx, launch_kernel(mode, generic_morph_kernel<C, RX, MAX>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
-                                dim3(kGenWarps * 32), smem_bytes, ctx->compute, *map, p, taps));
+    if constexpr (BPS == 1)
+        DIP_CUDA(ctx, launch_kernel(mode, generic_morph_kernel<C, RX, MAX>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
+                                    dim3(kGenWarps * 32), smem_bytes, ctx->compute, *map, p, taps));
+    else
+        DIP_CUDA(ctx, launch_kernel(mode, generic_morph16_kernel<C, RX, MAX>, dim3((unsigned)p.tiles_x, (unsigned)p.tiles_y, (unsigned)src->v.frames),
+                                    dim3(kGenWarps * 32), smem_bytes, ctx->compute, *map, p, taps));
     DIP_CHECK_LAUNCH(ctx, "generic_morph_kernel");
     return DIP_OK;
 }
@@ -344,6 +435,18 @@ int launch_generic_morph(dip_ctx* ctx, int rx, const dip_image* src, dip_image* 
     if (c == 3 && rx == 2) return launch_generic_morph_t<3, 2, MAX>(ctx, src, dst, g, taps);
     if (c == 4 && rx == 1) return launch_generic_morph_t<4, 1, MAX>(ctx, src, dst, g, taps);
     if (c == 4 && rx == 2) return launch_generic_morph_t<4, 2, MAX>(ctx, src, dst, g, taps);
+    return -1;
+}
+template <bool MAX>
+int launch_generic_morph16(dip_ctx* ctx, int rx, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
+    const int c = src->v.channels;
+    if (c == 1 && rx == 1) return launch_generic_morph_t<1, 1, MAX, 2>(ctx, src, dst, g, taps);
+    if (c == 1 && rx == 2) return launch_generic_morph_t<1, 2, MAX, 2>(ctx, src, dst, g, taps);
+    if (c == 1 && rx == 3) return launch_generic_morph_t<1, 3, MAX, 2>(ctx, src, dst, g, taps);
+    if (c == 3 && rx == 1) return launch_generic_morph_t<3, 1, MAX, 2>(ctx, src, dst, g, taps);
+    if (c == 3 && rx == 2) return launch_generic_morph_t<3, 2, MAX, 2>(ctx, src, dst, g, taps);
+    if (c == 4 && rx == 1) return launch_generic_morph_t<4, 1, MAX, 2>(ctx, src, dst, g, taps);
+    if (c == 4 && rx == 2) return launch_generic_morph_t<4, 2, MAX, 2>(ctx, src, dst, g, taps);
     return -1;
 }
 
@@ -397,6 +500,10 @@ bool generic_tiled_reach(const dip_image* src, int kw, int kh) {
 int launch_generic_tiled(dip_ctx* ctx, int mode, int kw, const dip_image* src, dip_image* dst, const RowGeom& g, const SmallTaps& taps) {
     const int rx = std::max(1, kw / 2);
     if (src->v.bps == 2) {
+        if (mode < 2 && !g_generic_float_morph) {   // minima straight on the packed 16-bit words
+            const int rc = mode == 0 ? launch_generic_morph16<false>(ctx, rx, src, dst, g, taps) : launch_generic_morph16<true>(ctx, rx, src, dst, g, taps);
+            if (rc != -1) return rc;
+        }
         switch (mode) {
             case 0: return launch_generic_tiled_16<0>(ctx, rx, src, dst, g, taps);
             case 1: return launch_generic_tiled_16<1>(ctx, rx, src, dst, g, taps);
