@@ -10,8 +10,8 @@
 // Copy, inversion, upload and download are byte-wise and run through the 8-bit paths unchanged (~x on the two bytes of a
 // sample is 65535 - x).  The reference itself only ever feeds 8-bit images (cv.imread without flags), so these are not
 // benchmark kernels: the stencils run on the tiled generic kernel (stencil_generic.cu, up to 7x7 taps where the
-// 16-byte tile halo reaches) and on the direct kernel below for anything larger; the two point operations here are
-// plain 16-byte-vector kernels.
+// 16-byte tile halo reaches; erosions / dilations as packed minima over the raw words) and on the direct kernel below
+// for anything larger; threshold is a variant of the flat point kernel (point_ops.cu), grayscale a 16-byte-vector kernel here.
 #include "dip_internal.h"
 
 namespace dip {
@@ -19,25 +19,6 @@ namespace dip {
 namespace {
 
 constexpr int kThreads = 256;
-
-// x > t ? maxval : 0 on packed 16-bit lanes
-__global__ void __launch_bounds__(kThreads) threshold16_kernel(ImgView src, ImgView dst, int vec_per_row, size_t total, uint32_t t2, uint32_t m2, bool exact) {
-    const size_t i = (size_t)blockIdx.x * kThreads + threadIdx.x;
-    pdl_launch_dependents();
-    pdl_wait();
-    if (i >= total) return;
-    const int vx = (int)(i % (size_t)vec_per_row);
-    const size_t q = i / (size_t)vec_per_row;
-    const int y = (int)(q % (size_t)src.height);
-    const size_t f = q / (size_t)src.height;
-    const uint4 v = *reinterpret_cast<const uint4*>(src.base + f * src.frame_stride + (size_t)y * src.pitch + 16 * vx);
-    uint4 o;
-    o.x = __vcmpgtu2(v.x, t2) & m2;
-    o.y = __vcmpgtu2(v.y, t2) & m2;
-    o.z = __vcmpgtu2(v.z, t2) & m2;
-    o.w = __vcmpgtu2(v.w, t2) & m2;
-    store16(dst.base + f * dst.frame_stride + (size_t)y * dst.pitch + 16 * vx, o, chunk_valid(16 * vx, src.rowbytes, exact));
-}
 
 // BT.601 in 15-bit fixed point like cv.cvtColor's 16-bit path, gray replicated into the colour channels.  A thread owns a
 // group of 8 (BGR) or 4 (BGRA) pixels = 48 / 32 bytes = whole 16-byte vectors; the last, partial group of a row goes
@@ -161,18 +142,6 @@ int launch_direct16_t(dip_ctx* ctx, const Direct16Params& p) {
 }
 
 }  // namespace
-
-int launch_threshold16(dip_ctx* ctx, const ImgView& src, const ImgView& dst, uint16_t thresh, uint16_t maxval) {
-    const int vpr = (src.rowbytes + 15) / 16;
-    const size_t total = (size_t)vpr * src.height * src.frames;
-    if (total == 0) return DIP_OK;
-    const size_t blocks = (total + kThreads - 1) / kThreads;
-    if (blocks > 0x7FFFFFFFull) return fail(ctx, DIP_ERR_UNSUPPORTED, "image stack too large for one launch");
-    DIP_CUDA(ctx, launch_kernel(plan_launch(ctx, src, dst), threshold16_kernel, dim3((unsigned)blocks), dim3(kThreads), 0, ctx->compute, src, dst, vpr, total,
-                                (uint32_t)thresh * 0x00010001u, (uint32_t)maxval * 0x00010001u, exact_rows(dst)));
-    DIP_CHECK_LAUNCH(ctx, "threshold16_kernel");
-    return DIP_OK;
-}
 
 int launch_grayscale16(dip_ctx* ctx, const ImgView& src, const ImgView& dst) {
     if (src.channels == 1) return launch_point(ctx, kCopy, src, dst, 0, 0);   // already gray: a byte-wise copy

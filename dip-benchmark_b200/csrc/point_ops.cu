@@ -41,6 +41,7 @@ __device__ __forceinline__ uint32_t luma(uint32_t px, uint32_t wlo, uint32_t whi
 constexpr int kGray4 = 3;       // BGRA -> Y,Y,Y,255
 constexpr int kMap = 4;         // any composition of the byte-wise ops (dip_internal.h: ByteMap)
 constexpr int kMapGray4 = 5;    // post(gray(pre(x))) on BGRA
+constexpr int kThreshold16 = 6; // x > t ? maxval : 0 on 16-bit samples (t4 / flip4 hold the value in both halves)
 
 // `m`: the threshold (t4, flip4 = maxval) or the map; `post`: second map of kMapGray4
 template <int OP>
@@ -48,6 +49,7 @@ __device__ __forceinline__ uint32_t point_word(uint32_t x, const MapParams& m, c
     if (OP == kCopy) return x;
     if (OP == kInvert) return ~x;
     if (OP == kThreshold) return __vcmpgtu4(x, m.t4) & m.flip4;
+    if (OP == kThreshold16) return __vcmpgtu2(x, m.t4) & m.flip4;
     if (OP == kMap) return map_word(x, m);
     if (OP == kMapGray4) x = map_word(x, m);
     const uint32_t y = luma(x, kWLo0, kWHi0);
@@ -307,6 +309,13 @@ int launch_point_t(dip_ctx* ctx, const ImgView& src, const ImgView& dst, const M
 }
 
 }  // namespace
+
+int launch_threshold16(dip_ctx* ctx, const ImgView& src, const ImgView& dst, uint16_t thresh, uint16_t maxval) {
+    MapParams m;
+    m.t4 = (uint32_t)thresh * 0x00010001u;
+    m.flip4 = (uint32_t)maxval * 0x00010001u;
+    return launch_point_t<kThreshold16>(ctx, src, dst, m);
+}
 
 int launch_point(dip_ctx* ctx, PointOp op, const ImgView& src, const ImgView& dst, uint8_t thresh, uint8_t maxval) {
     switch (op) {
