@@ -44,7 +44,8 @@ namespace {
 // "umma" 1 = the fused 1x5+5x1 Gaussian on the tensor cores (gauss_umma.cu: tcgen05.mma.kind::i8, bit-exact, but 15.9 us
 // per frame against 10.4 for the packed-half SIMD kernel so far -- profiles/r2_umma_experiment.md) instead of the SIMD kernel.
 // "fused_shape": band rows x warps (and a register cap) of the fused Gaussian -> erosion kernel on one-channel images (A/B only).
-struct Knobs { int tile_rows = 0; int int_math = 0; int direct_generic = 0; int umma = 0; int fused_shape = 0; };
+// "band_shape": rows per warp x warps per CTA of the 5-tap tiled kernels on 3-channel stacks (A/B only): 0 = 15 x 4.
+struct Knobs { int tile_rows = 0; int int_math = 0; int direct_generic = 0; int umma = 0; int fused_shape = 0; int band_shape = 0; };
 Knobs g_knobs;
 
 // One warp band of the fused Gaussian -> erosion kernel below.  EDGE: the tile touches the image rim, so Gaussian
@@ -250,6 +251,23 @@ int launch_tiled_c(dip_ctx* ctx, const dip_image* src, dip_image* dst, const Row
             const bool small = g_knobs.tile_rows ? g_knobs.tile_rows < 60 : tiles64 < 2ll * 6 * ctx->sm_count;
             // multiples of the window period (5 / 3 rows); measured best for one 3504x2336 image: 40- and 24-row tiles
             constexpr int kSmallR = op_taps(OP) == 2 ? 10 : 6;
+            if constexpr (OP == kConv5Sep || OP == kConv5) {
+                // Stacks run in the sustained power state (1 kW cap), where time follows the instructions executed, not
+                // the resident warps: 30-row bands on 2-warp CTAs (same 64-row tile) recompute 4 horizontal passes per 30
+                // rows instead of per 15 and are 3 % faster for the 1x5+5x1 kernel there (tools/sustained_op.py,
+                // profiles/r2_sustained_shapes.md) although slower in a cold burst; 5x5 is best at 15 x 4.
+                if (!small && OP == kConv5Sep && g_knobs.band_shape == 0) return launch_tiled<OP, 3, 30, 2, false>(ctx, src, dst, g, nullptr);
+                if (!small) switch (g_knobs.band_shape) {
+                    case 1: return launch_tiled<OP, 3, 30, 2, false>(ctx, src, dst, g, nullptr);
+                    case 7: return launch_tiled<OP, 3, 15, 4, false>(ctx, src, dst, g, nullptr);
+                    case 2: return launch_tiled<OP, 3, 30, 4, false>(ctx, src, dst, g, nullptr);
+                    case 3: return launch_tiled<OP, 3, 45, 2, false>(ctx, src, dst, g, nullptr);
+                    case 4: return launch_tiled<OP, 3, 60, 2, false>(ctx, src, dst, g, nullptr);
+                    case 5: return launch_tiled<OP, 3, 20, 3, false>(ctx, src, dst, g, nullptr);
+                    case 6: return launch_tiled<OP, 3, 60, 1, false>(ctx, src, dst, g, nullptr);
+                    default: break;
+                }
+            }
             return small ? launch_tiled<OP, 3, kSmallR, 4, false>(ctx, src, dst, g, nullptr) : launch_tiled<OP, 3, 15, 4, false>(ctx, src, dst, g, nullptr);
         }
     }
@@ -587,9 +605,15 @@ int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, co
                 case 8: return launch_fused_g5e3<1, 15, 4, false, 0, 1>(ctx, src, dst, g, nullptr);
                 case 9: return launch_fused_g5e3<1, 15, 4, false, 0, 15>(ctx, src, dst, g, nullptr);
                 case 10: return launch_fused_g5e3<1, 15, 4, false, 0, 3>(ctx, src, dst, g, nullptr);
+                case 11: return launch_fused_g5e3<1, 60, 2, false>(ctx, src, dst, g, nullptr);
+                case 12: return launch_fused_g5e3<1, 60, 1, false>(ctx, src, dst, g, nullptr);
+                case 13: return launch_fused_g5e3<1, 45, 3, false>(ctx, src, dst, g, nullptr);
                 default: break;
             }
-            return mapped ? launch_fused_g5e3<1, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<1, 15, 4, false>(ctx, src, dst, g, nullptr);
+            // 30-row bands on 2-warp CTAs: 36 horizontal passes per 30 output rows instead of 21 per 15; 4.6 % faster in the
+            // sustained power state (profiles/r2_sustained_shapes.md); fused_shape 14 = the 15 x 4 shape for A/B
+            if (!mapped && g_knobs.fused_shape == 14) return launch_fused_g5e3<1, 15, 4, false>(ctx, src, dst, g, nullptr);
+            return mapped ? launch_fused_g5e3<1, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<1, 30, 2, false>(ctx, src, dst, g, nullptr);
         case 3: return mapped ? launch_fused_g5e3<3, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<3, 15, 4, false>(ctx, src, dst, g, nullptr);
         case 4: return mapped ? launch_fused_g5e3<4, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<4, 15, 4, false>(ctx, src, dst, g, nullptr);
     }
@@ -632,6 +656,7 @@ int dip_debug_set(const char* key, int value) {
     else if (!strcmp(key, "direct_generic")) g_knobs.direct_generic = value;
     else if (!strcmp(key, "umma")) g_knobs.umma = value;
     else if (!strcmp(key, "fused_shape")) g_knobs.fused_shape = value;
+    else if (!strcmp(key, "band_shape")) g_knobs.band_shape = value;
     else if (!strcmp(key, "float_morph")) g_generic_float_morph = value != 0;
     else if (!strcmp(key, "no_pad")) g_no_occupancy_pad = value != 0;
     else return fail(nullptr, DIP_ERR_ARG, "unknown knob %s", key);

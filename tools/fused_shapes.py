@@ -8,7 +8,8 @@ dip = load(); L = dip.lib()
 ctx = dip.Context(0)
 fused = dip.make_op("gauss5x5_erode3x3")
 shapes = [int(a) for a in sys.argv[1:]] or [0, 1, 2, 3, 4, 5, 6, 7]
-names = {0: "15 rows x 4 warps (shipped)", 1: "30 x 2", 2: "30 x 4", 3: "15 x 4, 5 CTAs/SM by registers", 4: "15 x 2", 5: "30 x 3", 6: "15 x 4, 6 CTAs/SM by registers", 7: "45 x 2", 8: "15 x 4, row loop not unrolled", 9: "15 x 4, row loop unrolled 15x", 10: "15 x 4, row loop unrolled 3x"}
+WARM, TIMED = int(os.environ.get("FUSED_WARM", "60")), int(os.environ.get("FUSED_TIMED", "20"))   # 1000 / 400: the sustained power state
+names = {0: "15 rows x 4 warps (shipped)", 1: "30 x 2", 2: "30 x 4", 3: "15 x 4, 5 CTAs/SM by registers", 4: "15 x 2", 5: "30 x 3", 6: "15 x 4, 6 CTAs/SM by registers", 7: "45 x 2", 8: "15 x 4, row loop not unrolled", 9: "15 x 4, row loop unrolled 15x", 10: "15 x 4, row loop unrolled 3x", 11: "60 x 2", 12: "60 x 1", 13: "45 x 3"}
 w, h = 65536, 16384
 src = ctx.image(w, h, 1).synth_fill(seed=1); dst = ctx.image(w, h, 1)
 L.dip_debug_set(b"fused_shape", 0)
@@ -20,10 +21,10 @@ for rnd in range(4):
         L.dip_debug_set(b"fused_shape", s)
         ctx.apply(fused, src, dst)
         assert dst.checksum() == want, f"shape {s} differs"
-        for _ in range(60): ctx.apply(fused, src, dst)
+        for _ in range(WARM): ctx.apply(fused, src, dst)
         ctx.timer_start()
-        for _ in range(20): ctx.apply(fused, src, dst)
-        res[s].append(ctx.timer_stop() / 20)
+        for _ in range(TIMED): ctx.apply(fused, src, dst)
+        res[s].append(ctx.timer_stop() / TIMED)
 print("| fused_shape | ms per 65536x16384 band, min / median | GB/s (2 B/pixel) | fraction of 6459 |")
 print("|---|---|---|---|")
 for s in shapes:
