@@ -60,7 +60,7 @@ __host__ __device__ constexpr int op_min_ctas(int op) { return op == kConv5Sep ?
 #endif
 constexpr int kEvenPrmt5 = DIP_EVEN_PRMT5;  // packed-half 1x5+5x1: words per row whose even bytes come from a PRMT
 #ifndef DIP_CASCADE_HALF
-#define DIP_CASCADE_HALF 8
+#define DIP_CASCADE_HALF 6
 #endif
 constexpr int kCascadeHalf = DIP_CASCADE_HALF;  // packed-half 1x5+5x1: packed lanes (of 8) whose vertical pass is the all-half cascade
 
@@ -263,29 +263,10 @@ constexpr uint32_t kH16th = 0x2C002C00u;     // half2(1/16)
 constexpr uint32_t kHNeg2048u = 0x88008800u; // half2(-2048 * 2^-24) = -2^-13
 constexpr uint32_t kH128u = 0x00800080u;     // half2(128 * 2^-24): the bit pattern of the byte 128
 // RNE((a + 4 b + 6 c + 4 d + e) / 16) per lane; ae = a + e and bd = b + d are plain integer sums (<= 510)
-// RNE((a + 4 b + 6 c + 4 d + e) / 16) per lane, from the five byte patterns, in FIVE instructions:
-//   S - 2048 = (a + e + 2 c - 2048) + 4 (b + c + d).
-// The first bracket needs no half arithmetic at all: for 0 <= t <= 1020 the half (t - 2048) u has the bit pattern
-// 0x8800 - t (sign, exponent 1, mantissa 1024 - t: the binade [1024, 2048) u has ulp u), so K = 0x8800 - a - e - 2 c is two
-// 3-input integer subtractions per packed pair (no borrow leaves a lane: t <= 1020 < 0x8800).  v = b + c + d <= 765 is one
-// 3-input add and still a (subnormal) half, 4 v + K lies in [-2048, 2032] and is exact, and the rounding FMA is the old one.
-// `addend` = 128 u gives the u8 result as the lane's bit pattern; 0 gives the half (result - 128) u (see "vertical cascade").
-// (Before: a + e and b + d as integers, then 6 c - 2048, + 4 (b + d), + (a + e) as three half operations: six in all.)
-constexpr uint32_t kHNeg2048Pat = 0x88008800u;
-// x - a - b as ONE 3-input add with two negated operands (written in PTX: the front end would re-associate the C
-// expression into (a + e + 2 c) followed by a subtraction from the constant, one instruction more)
-__device__ __forceinline__ uint32_t sub3(uint32_t x, uint32_t a, uint32_t b) {
-    uint32_t r;
-    asm("{\n.reg .u32 t;\nsub.u32 t, %1, %2;\nsub.u32 %0, t, %3;\n}" : "=r"(r) : "r"(x), "r"(a), "r"(b));
-    return r;
-}
-__device__ __forceinline__ uint32_t half_gauss5(uint32_t a, uint32_t e, uint32_t b, uint32_t d, uint32_t c, uint32_t addend = kH128u) {
-    // (a + e + 2 c - 2048) u as a half: C - a - e (one 3-input add), then - 2 c as a multiply-add (32-bit arithmetic is
-    // linear over the two lanes and every lane's final value is in range, so transient borrows cancel)
-    uint32_t k;
-    asm("mad.lo.u32 %0, %1, 0xFFFFFFFE, %2;" : "=r"(k) : "r"(c), "r"(sub3(kHNeg2048Pat, a, e)));
-    const uint32_t v = b + c + d;
-    return hfma2(hfma2(v, kH4, k), kH16th, addend);
+// `addend` = 128 u gives the u8 result as the lane's bit pattern; 0 gives the half (result - 128) u (see "vertical cascade")
+__device__ __forceinline__ uint32_t half_gauss5(uint32_t ae, uint32_t bd, uint32_t c, uint32_t addend = kH128u) {
+    const uint32_t s = hadd2(hfma2(bd, kH4, hfma2(c, kH6, kHNeg2048u)), ae);  // S - 2048, exact
+    return hfma2(s, kH16th, addend);
 }
 // RNE((a + 2 b + c) / 4) per lane; ac = a + c (<= 510)
 __device__ __forceinline__ uint32_t half_gauss3(uint32_t ac, uint32_t b) { return hmul2(hfma2(b, kH2, ac), kHQuarter); }
@@ -294,8 +275,8 @@ __device__ __forceinline__ uint32_t half_gauss3(uint32_t ac, uint32_t b) { retur
 template <int C, int CENTRED = 0>
 __device__ __forceinline__ void hgauss5_half(const Row8& r, Acc8& h) {
 #define DIP_H5H(j)                                                                                                   \
-    h.v[2 * j] = half_gauss5(pair_at<4 * j - 2 * C>(r), pair_at<4 * j + 2 * C>(r), pair_at<4 * j - C>(r), pair_at<4 * j + C>(r), r.e[2 + j], 2 * j < CENTRED ? 0u : kH128u); \
-    h.v[2 * j + 1] = half_gauss5(pair_at<4 * j + 1 - 2 * C>(r), pair_at<4 * j + 1 + 2 * C>(r), pair_at<4 * j + 1 - C>(r), pair_at<4 * j + 1 + C>(r), r.o[2 + j], 2 * j + 1 < CENTRED ? 0u : kH128u);
+    h.v[2 * j] = half_gauss5(pair_at<4 * j - 2 * C>(r) + pair_at<4 * j + 2 * C>(r), pair_at<4 * j - C>(r) + pair_at<4 * j + C>(r), r.e[2 + j], 2 * j < CENTRED ? 0u : kH128u); \
+    h.v[2 * j + 1] = half_gauss5(pair_at<4 * j + 1 - 2 * C>(r) + pair_at<4 * j + 1 + 2 * C>(r), pair_at<4 * j + 1 - C>(r) + pair_at<4 * j + 1 + C>(r), r.o[2 + j], 2 * j + 1 < CENTRED ? 0u : kH128u);
     DIP_H5H(0) DIP_H5H(1) DIP_H5H(2) DIP_H5H(3)
 #undef DIP_H5H
 }
@@ -495,7 +476,7 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
                 load_own(colp + (i + 4) * kRowBytes, w4);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    res[k] = half_gauss5(w0.v[k], w4.v[k], w1.v[k], w3.v[k], w2.v[k]);
+                    res[k] = half_gauss5(w0.v[k] + w4.v[k], w1.v[k] + w3.v[k], w2.v[k]);
                 w0 = w1; w1 = w2; w2 = w3; w3 = w4;
             }
             uint4 o;
