@@ -934,6 +934,21 @@ PFN_streamWaitValue32 stream_wait_value_fn() {
     return fn;
 }
 
+typedef CUresult (*PFN_streamWriteValue32)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+PFN_streamWriteValue32 stream_write_value_fn() {
+    static PFN_streamWriteValue32 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        const char* e = getenv("DIP_FLAG_SIGNAL_KERNEL");   // 1: always signal with the one-thread kernel (A/B)
+        if (e && e[0] == '1') return;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuStreamWriteValue32", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_streamWriteValue32>(p);
+    });
+    return fn;
+}
+
 int flag_word(dip_ctx* ctx, const dip_image* flags, int index, uint32_t** word) {
     if (!ctx || !flags) return fail(ctx, DIP_ERR_ARG, "null argument");
     if (index < 0 || (size_t)(index + 1) * 4 > (size_t)flags->v.rowbytes) return fail(ctx, DIP_ERR_ARG, "flag index %d out of range", index);
@@ -960,6 +975,17 @@ int dip_flag_signal(dip_ctx* ctx, dip_image* flags, int index, uint32_t value) {
     if (rc != DIP_OK) return rc;
     DIP_CUDA(ctx, cudaSetDevice(ctx->device));
     dep_touch(ctx);
+    // A stream memory operation where the driver takes it for this address (the default flags put a system-scope fence in
+    // front of the write, and as a stream operation it runs after every earlier kernel of the stream has finished): no
+    // launch at all.  Otherwise -- some drivers refuse peer / IPC-mapped addresses -- a one-thread kernel with a release store.
+    if (!ctx->capturing && ctx->flag_write_ok) {
+        if (PFN_streamWriteValue32 fn = stream_write_value_fn()) {
+            if (fn(reinterpret_cast<CUstream>(ctx->compute), reinterpret_cast<CUdeviceptr>(word), value, 0x0 /* CU_STREAM_WRITE_VALUE_DEFAULT */) == CUDA_SUCCESS)
+                return DIP_OK;
+            cudaGetLastError();
+        }
+        ctx->flag_write_ok = false;   // not again on this ctx
+    }
     flag_signal_kernel<<<1, 1, 0, ctx->compute>>>(word, value);  // plain launch: runs after every earlier kernel of the stream has finished
     DIP_CHECK_LAUNCH(ctx, "flag_signal_kernel");
     return DIP_OK;

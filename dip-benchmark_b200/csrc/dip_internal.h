@@ -143,6 +143,7 @@ struct dip_ctx {
     dip::CaptureTracker cap;
     uint64_t capture_launches0 = 0;
     void* jpeg = nullptr;                // jpeg.cu's codec state (nvJPEG handles), created on first use
+    bool flag_write_ok = true;           // dip_flag_signal: cuStreamWriteValue32 has not been refused on this ctx
     std::string last_error;
 };
 

@@ -377,6 +377,8 @@ DIP_API int dip_apply_rows_peer(dip_ctx* ctx, const dip_op* op, const dip_image*
  * _import (width 4*count, height 1, 1 channel).
  *   dip_flag_signal: after everything enqueued so far on the compute stream has finished, store `value` into word
  *                    `index` (release, system scope); `flags` may be the neighbour's mapped array (a store over NVLink).
+ *                    A stream memory operation (cuStreamWriteValue32) where the driver accepts the address, else a
+ *                    one-thread kernel.
  *   dip_flag_wait:   the compute stream waits until word `index` >= value (cuStreamWaitValue32 -- a stream operation,
  *                    no kernel spins); `flags` must live on this ctx's GPU.
  *   dip_flag_read:   host read-back (synchronous), for tests.
