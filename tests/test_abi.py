@@ -100,6 +100,31 @@ def test_both_bench_arms_describe_the_same_config():
     assert src.count('"config": config_dict(args.batch)') == 2   # one per arm, nothing arm-specific inside
 
 
+def test_bench_reads_traffic_from_the_committed_ncu_capture_and_parses_clock_samples():
+    """bench.py's roofline.traffic comes from the newest profiles/r*_ncu_full.json (not a constant), and its clock sampler
+    turns nvidia-smi rows into the `clocks` object (median under load, reasons) for the timed window only."""
+    import importlib.util
+    import json
+    import time
+    spec = importlib.util.spec_from_file_location("bench_mod2", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    per_frame, src = bench.ncu_traffic_per_frame("convolution-gaussian-blur-5x5-separated")
+    assert src.startswith("profiles/") and src.endswith("_ncu_full.json")
+    cap = json.load(open(os.path.join(ROOT, src)))
+    k = [x for x in cap["kernels"] if x.get("op") == "convolution-gaussian-blur-5x5-separated"][0]
+    assert per_frame == (k["dram_read_bytes"] + k["dram_write_bytes"]) / cap["frames"]
+    assert 0.9 < per_frame / (2 * bench.FRAME_BYTES) < 1.1           # measured DRAM traffic ~ algorithmic bytes
+    assert bench.ncu_traffic_per_frame("no-such-op")[0] is None
+    cs = bench.ClockSampler(0)
+    now = time.time()
+    cs.t0, cs.t1 = now - 1.0, now
+    row = lambda mhz, cap_: [str(mhz), "1965", "998.5", "0x4", "Not Active", "Not Active", "Not Active", cap_]   # noqa: E731
+    cs.rows = [(now - 5.0, row(1965, "Not Active")), (now - 0.8, row(1530, "Active")), (now - 0.5, row(1545, "Active")), (now - 0.2, row(1560, "Active"))]
+    out = cs.summary()
+    assert out == {"sm_mhz": 1545.0, "sm_max_mhz": 1965.0, "power_w_max": 998.5, "reasons": ["sw_power_cap"], "samples": 3, "window": "timed region"}
+
+
 def test_chain_planner_counts_passes_without_a_gpu():
     """dip_chain_passes is host logic: byte-wise runs fold into one map that rides on a neighbouring tiled kernel."""
     import numpy as np
