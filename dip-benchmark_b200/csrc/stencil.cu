@@ -614,7 +614,9 @@ int stencil_gauss5_erode3(dip_ctx* ctx, const dip_image* src, dip_image* dst, co
             // sustained power state (profiles/r2_sustained_shapes.md); fused_shape 14 = the 15 x 4 shape for A/B
             if (!mapped && g_knobs.fused_shape == 14) return launch_fused_g5e3<1, 15, 4, false>(ctx, src, dst, g, nullptr);
             return mapped ? launch_fused_g5e3<1, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<1, 30, 2, false>(ctx, src, dst, g, nullptr);
-        case 3: return mapped ? launch_fused_g5e3<3, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<3, 15, 4, false>(ctx, src, dst, g, nullptr);
+        case 3:
+            if (!mapped && g_knobs.fused_shape == 1) return launch_fused_g5e3<3, 30, 2, false>(ctx, src, dst, g, nullptr);   // A/B
+            return mapped ? launch_fused_g5e3<3, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<3, 15, 4, false>(ctx, src, dst, g, nullptr);
         case 4: return mapped ? launch_fused_g5e3<4, 15, 4, true>(ctx, src, dst, g, maps) : launch_fused_g5e3<4, 15, 4, false>(ctx, src, dst, g, nullptr);
     }
     return fail(ctx, DIP_ERR_ARG, "bad channel count");
