@@ -334,8 +334,16 @@ int dip_jpeg_decode_batch(dip_ctx* ctx, const uint8_t* const* data, const size_t
     if (want == 1) {
         work(0);
     } else {
+        // the workers take streams from a shared counter, so any number of them finishes the batch: if the host refuses a
+        // thread (no exception may cross the C boundary) the ones that started, and this thread, do its share
         std::vector<std::thread> threads;
-        for (int t = 1; t < want; ++t) threads.emplace_back(work, t);
+        for (int t = 1; t < want; ++t) {
+            try {
+                threads.emplace_back(work, t);
+            } catch (...) {
+                break;
+            }
+        }
         work(0);
         for (auto& th : threads) th.join();
     }
