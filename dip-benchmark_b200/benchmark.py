@@ -56,28 +56,39 @@ def parse_dir(string: str) -> str:                                # opencv:17-23
     return string
 
 
-def measure_time(func: Callable[[], Any], rounds: int, sync: Callable[[], Any] | None = None) -> tuple[float, float]:
-    """opencv:26-38; ``sync`` (if given) runs after the single call and after the loop."""
+def measure_time(func: Callable[[], Any], rounds: int, sync: Callable[[], Any] | None = None,
+                 record: Callable[[Callable[[], Any], int], Any] | None = None, block: int = 0) -> tuple[float, float]:
+    """opencv:26-38; ``sync`` (if given) runs after the single call and after the loop.  With ``record`` and ``block`` the
+    loop's calls are recorded ``block`` at a time into a CUDA graph (dip_graph_*) and replayed: ``rounds // block`` launches
+    plus the remainder as plain calls -- the same ``rounds`` executions of ``func``'s device work, one host call per block."""
     time_start_once = perf_counter()
     func()
     if sync:
         sync()
     time_end_once = perf_counter()
 
+    graph = record(func, block) if (record and block > 1 and rounds >= block) else None   # recorded outside the timed loop, like a warm-up
     _round = 0
     time_start_times = perf_counter()
+    if graph is not None:
+        while _round + block <= rounds:
+            graph.launch()
+            _round += block
     while _round < rounds:
         func()
         _round += 1
     if sync:
         sync()
     time_end_times = perf_counter()
+    if graph is not None:
+        graph.close()
     return (time_end_once - time_start_once, (time_end_times - time_start_times) / rounds)
 
 
 def perform_benchmark(cpu_image: np.ndarray, filename: str, dir: str, rounds: int, device: int = 0,
-                      sync_every_call: bool = False, out=print) -> dict[str, np.ndarray]:
-    """opencv:41-114.  Returns {prefix: output array} in addition to writing the files."""
+                      sync_every_call: bool = False, out=print, graph_block: int = 0) -> dict[str, np.ndarray]:
+    """opencv:41-114.  Returns {prefix: output array} in addition to writing the files.  ``graph_block`` > 1 replays the
+    device operations' loops from CUDA graphs of that many calls (transfers cannot be recorded and stay plain calls)."""
     ctx = _ops.Context(device)
     image = ctx.from_array(cpu_image)            # cv.UMat(cpu_image)   opencv:42
     sample = ctx.from_array(cpu_image)           #                      opencv:44 (aux is not needed: fused separable ops)
@@ -101,8 +112,21 @@ def perform_benchmark(cpu_image: np.ndarray, filename: str, dir: str, rounds: in
 
     biggest_description_length = max(len(desc) for desc, _, _ in operations)
     outputs: dict[str, np.ndarray] = {}
+    def record(func, block):
+        try:
+            ctx.graph_begin()
+            for _ in range(block):
+                func()
+            return ctx.graph_end()
+        except _ops.capi.DipError:      # not recordable (a transfer, or a sync after every call): plain calls
+            try:
+                ctx.graph_end()
+            except _ops.capi.DipError:
+                pass
+            return None
+
     for description, prefix, func in operations:                                            # opencv:109-114
-        time_once, time_rounds = measure_time(func, rounds, ctx.sync)
+        time_once, time_rounds = measure_time(func, rounds, ctx.sync, record if (graph_block > 1 and prefix and not sync_every_call) else None, graph_block)
         out(f"| {description: <{biggest_description_length}} | {time_once:10.6f}s (once) | {time_rounds:10.6f}s ({rounds} times) |")
         output_image = sample.download().reshape(cpu_image.shape)
         outputs[prefix] = output_image
@@ -121,8 +145,9 @@ def main(argv=None):
     parser.add_argument("--rounds", type=int, default=10000, help="Times to be executed, default 10000")
     parser.add_argument("--device", type=int, default=0)
     parser.add_argument("--sync", action="store_true", help="wait after every call (SYCL backend semantics)")
+    parser.add_argument("--graph", type=int, default=0, metavar="N", help="replay the device operations' loops from CUDA graphs of N calls")
     args = parser.parse_args(argv)
-    perform_benchmark(args.infile[0], args.infile[1], args.outdir, args.rounds, args.device, args.sync)
+    perform_benchmark(args.infile[0], args.infile[1], args.outdir, args.rounds, args.device, args.sync, graph_block=args.graph)
 
 
 if __name__ == "__main__":

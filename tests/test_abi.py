@@ -71,6 +71,21 @@ def test_measure_time_mirrors_the_reference_loop(dip):
     calls, syncs = [], []
     once, avg = benchmark.measure_time(lambda: calls.append(1), 7, lambda: syncs.append(1))
     assert len(calls) == 8 and len(syncs) == 2 and once >= 0 and avg >= 0
+    # recorded in blocks: 23 rounds = 1 cold call + 3 recorded while building the graph + 7 replays of 3 + 2 plain calls
+    class G:
+        launches, closed = 0, False
+        def launch(self): G.launches += 1
+        def close(self): G.closed = True
+    calls.clear()
+    def record(func, block):
+        for _ in range(block):
+            func()
+        return G()
+    benchmark.measure_time(lambda: calls.append(1), 23, None, record, 3)
+    assert (len(calls), G.launches, G.closed) == (1 + 3 + 2, 7, True)
+    calls.clear()
+    benchmark.measure_time(lambda: calls.append(1), 5, None, lambda f, b: None, 3)   # not recordable: plain calls
+    assert len(calls) == 6
 
 
 def test_bench_reference_arm_prints_one_json_line():

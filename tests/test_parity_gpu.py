@@ -466,6 +466,12 @@ def test_python_perform_benchmark_mirror(ctx, dip, orc, tmp_path, capsys):
     for prefix, ofn in orc.OPERATIONS:
         assert np.array_equal(outs[prefix], ofn(img)), prefix
         assert os.path.exists(tmp_path / f"{prefix}-t.png")
+    # the loops replayed from CUDA graphs of 4 calls (--graph 4): same rows, same results
+    lines2 = []
+    outs2 = benchmark.perform_benchmark(img, "g.png", str(tmp_path), 10, out=lines2.append, graph_block=4)
+    assert len(lines2) == 14
+    for prefix, ofn in orc.OPERATIONS:
+        assert np.array_equal(outs2[prefix], ofn(img)), prefix
 
 
 def test_wrapped_regions_of_interest_with_foreign_pitch(ctx, dip, orc):
