@@ -268,12 +268,40 @@ __device__ __forceinline__ uint32_t half_gauss5(uint32_t ae, uint32_t bd, uint32
     const uint32_t s = hadd2(hfma2(bd, kH4, hfma2(c, kH6, kHNeg2048u)), ae);  // S - 2048, exact
     return hfma2(s, kH16th, addend);
 }
+// The same in FIVE instructions from the five byte patterns: S - 2048 = (a + e + 2 c - 2048) + 4 (b + c + d).  The first
+// bracket needs no half arithmetic: for 0 <= t <= 1020 the half (t - 2048) u has the bit pattern 0x8800 - t (sign, exponent 1,
+// mantissa 1024 - t: the binade [1024, 2048) u has ulp u), so K = 0x8800 - a - e - 2 c is one 3-input add with two negated
+// operands and one multiply-add per packed pair (32-bit arithmetic is linear over the two lanes and every lane's final value is
+// in range, so transient borrows cancel).  v = b + c + d <= 765 is one 3-input add and still a (subnormal) half; 4 v + K lies in
+// [-2048, 2032] and is exact.  Used by the 2-warp stack shape only: under the 80-register cap of the 4-warp shapes it spills
+// (one image per call 3.5 % slower, profiles/r2_cascade_ab.md); on stacks it is neutral in time and 4 % fewer instructions.
+__device__ __forceinline__ uint32_t sub3(uint32_t x, uint32_t a, uint32_t b) {   // x - a - b (written in PTX: the front end re-associates the C expression)
+    uint32_t r;
+    asm("{\n.reg .u32 t;\nsub.u32 t, %1, %2;\nsub.u32 %0, t, %3;\n}" : "=r"(r) : "r"(x), "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t half_gauss5_v2(uint32_t a, uint32_t e, uint32_t b, uint32_t d, uint32_t c, uint32_t addend) {
+    uint32_t k;
+    asm("mad.lo.u32 %0, %1, 0xFFFFFFFE, %2;" : "=r"(k) : "r"(c), "r"(sub3(kHNeg2048u, a, e)));   // kHNeg2048u = 0x88008800
+    const uint32_t v = b + c + d;
+    return hfma2(hfma2(v, kH4, k), kH16th, addend);
+}
+
 // RNE((a + 2 b + c) / 4) per lane; ac = a + c (<= 510)
 __device__ __forceinline__ uint32_t half_gauss3(uint32_t ac, uint32_t b) { return hmul2(hfma2(b, kH2, ac), kHQuarter); }
 
 // CENTRED: the first CENTRED packed results come out as halves (result - 128) u instead of byte patterns
-template <int C, int CENTRED = 0>
+// FIVE: the five-instruction form (half_gauss5_v2)
+template <int C, int CENTRED = 0, bool FIVE = false>
 __device__ __forceinline__ void hgauss5_half(const Row8& r, Acc8& h) {
+    if constexpr (FIVE) {
+#define DIP_H5V(j)                                                                                                   \
+    h.v[2 * j] = half_gauss5_v2(pair_at<4 * j - 2 * C>(r), pair_at<4 * j + 2 * C>(r), pair_at<4 * j - C>(r), pair_at<4 * j + C>(r), r.e[2 + j], 2 * j < CENTRED ? 0u : kH128u); \
+    h.v[2 * j + 1] = half_gauss5_v2(pair_at<4 * j + 1 - 2 * C>(r), pair_at<4 * j + 1 + 2 * C>(r), pair_at<4 * j + 1 - C>(r), pair_at<4 * j + 1 + C>(r), r.o[2 + j], 2 * j + 1 < CENTRED ? 0u : kH128u);
+        DIP_H5V(0) DIP_H5V(1) DIP_H5V(2) DIP_H5V(3)
+#undef DIP_H5V
+        return;
+    }
 #define DIP_H5H(j)                                                                                                   \
     h.v[2 * j] = half_gauss5(pair_at<4 * j - 2 * C>(r) + pair_at<4 * j + 2 * C>(r), pair_at<4 * j - C>(r) + pair_at<4 * j + C>(r), r.e[2 + j], 2 * j < CENTRED ? 0u : kH128u); \
     h.v[2 * j + 1] = half_gauss5(pair_at<4 * j + 1 - 2 * C>(r) + pair_at<4 * j + 1 + 2 * C>(r), pair_at<4 * j + 1 - C>(r) + pair_at<4 * j + 1 + C>(r), r.o[2 + j], 2 * j + 1 < CENTRED ? 0u : kH128u);
@@ -557,12 +585,13 @@ __device__ __forceinline__ void compute_band(const uint8_t* colp, uint8_t* dptr,
         //   * the other lanes keep byte patterns, add p, v, q (<= 2040: still bit patterns of halves) on the integer ALU
         //     pipe and centre q with one HADD2: 3 IADD + 2 HADD2 + HFMA2, for the balance between the two pipes.
         // (The window form before this was 2 IADD + 3 HFMA2/HADD2 + the rounding HFMA2 per lane.)
-        constexpr int NH = kCascadeHalf;
+        constexpr bool kFive = R == 30;               // the 2-warp stack shape (launch_tiled_c): five-instruction horizontal pass, all lanes on the half cascade
+        constexpr int NH = kFive ? 8 : kCascadeHalf;
         Acc8 H, P, V, Q, h;
         Row8 row;
         auto hpass = [&](const uint8_t* rp, Acc8& o) {
             load_row<PRE, kEvenPrmt5>(rp, row, &p);
-            hgauss5_half<C, NH>(row, o);
+            hgauss5_half<C, NH, kFive>(row, o);
         };
         auto add = [&](int k, uint32_t a, uint32_t b) { return k < NH ? hadd2(a, b) : a + b; };
         hpass(colp, H);
