@@ -133,6 +133,26 @@ def test_numpy_restatement_of_half_precision_cascade():
     assert np.array_equal(res, np.rint(S / 16.0).astype(np.int64))
 
 
+def test_numpy_restatement_of_the_five_instruction_gaussian():
+    """The horizontal [1 4 6 4 1] / 16 pass of the 2-warp stack shape (stencil_tiled.cuh, half_gauss5_v2):
+    S - 2048 = (a + e + 2c - 2048) + 4 (b + c + d).  For 0 <= t <= 1020 the half (t - 2048) u has the bit pattern 0x8800 - t, so
+    the first bracket is integer arithmetic on the byte patterns; 4 v + K is exact in half precision and one fused multiply-add
+    rounds S / 16 half to even (addend 128 u) or delivers the centred row (addend 0)."""
+    u = np.float64(2.0 ** -24)
+    t = np.arange(0, 1021)
+    assert np.array_equal((0x8800 - t).astype(np.uint16).view(np.float16).astype(np.float64) / u, t - 2048)
+    rng = np.random.default_rng(11)
+    a, b, c, d, e = rng.integers(0, 256, (5, 300000))
+    a[:4], b[:4], c[:4], d[:4], e[:4] = [0, 255, 0, 255], [0, 255, 255, 0], [0, 255, 0, 255], [0, 255, 255, 0], [0, 255, 0, 255]
+    K = (0x8800 - a - e - 2 * c).astype(np.uint16).view(np.float16)
+    v = (b + c + d).astype(np.uint16).view(np.float16)                    # <= 765: a subnormal half, bit pattern = value
+    y = (v.astype(np.float64) * 4 + K.astype(np.float64)).astype(np.float16)   # the FMA: exact product and sum, one rounding
+    S = a + 4 * b + 6 * c + 4 * d + e
+    assert np.array_equal(y.astype(np.float64) / u, S - 2048)
+    assert np.array_equal((y.astype(np.float64) / 16 + 128 * u).astype(np.float16).view(np.uint16), np.rint(S / 16.0).astype(np.int64))
+    assert np.array_equal((y.astype(np.float64) / 16).astype(np.float16).astype(np.float64) / u, np.rint(S / 16.0) - 128)
+
+
 def test_row_addressed_synth_and_checksum_compose(orc):
     """Bands of a mosaic: synth_rows stitches to the whole, band checksums add up to the whole's."""
     whole = orc.synth(64, 50, 1, seed=3, frame=0)
