@@ -394,8 +394,10 @@ DIP_API int dip_flag_read(dip_ctx* ctx, const dip_image* flags, int index, uint3
  * keys: "tile_rows" (stencil tile height: 0 = automatic, >= 60 the stack tiles, < 60 the single-image tiles),
  * "no_pad" (1 = do not pad shared memory to limit the resident tiles of the HBM-bound stencils), "int_math" (1 = the
  * packed-integer forms of the separable Gaussians instead of the packed-half ones), "umma" (1 = the fused 1x5+5x1
- * Gaussian on the tensor cores), "direct_generic" (1 = small arbitrary masks on the direct kernel), "fused_shape"
- * (band shape of the fused Gaussian -> erosion kernel on one-channel images).  Not needed by applications. */
+ * Gaussian on the tensor cores), "direct_generic" (1 = small arbitrary masks / kernels on the direct kernel),
+ * "float_morph" (1 = arbitrary masks on the fp32 tiled kernel instead of packed minima), "band_shape" (rows x warps of
+ * the 5-tap kernels on RGB stacks: 0 = shipped, 7 = 15 x 4, 1..6 = other shapes), "fused_shape" (band shape / unrolling
+ * of the fused Gaussian -> erosion kernel on one-channel images: 0 = shipped, 14 = 15 x 4).  Not needed by applications. */
 DIP_API int dip_debug_set(const char* key, int value);
 
 #ifdef __cplusplus
